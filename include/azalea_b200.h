@@ -1,0 +1,235 @@
+/*
+ * azalea_b200.h -- C ABI of the B200-native Azalea self-play search engine.
+ *
+ * The reference (jseppanen/azalea) is pure Python + Numba and has no FFI for
+ * this path; these entry points are what a binding for it would call, one
+ * per reference function on the hot path.  Each cites
+ * the reference file:line it replaces.  INTEGRATION.md shows the ctypes stub
+ * a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types.
+ *  - `*_dev` pointers are device pointers, everything else is host memory.
+ *  - every op enqueues work on `stream` (a cudaStream_t passed as void*, NULL
+ *    = legacy default stream) and returns without synchronising.
+ *  - return value: 0 = ok, negative = AZ_E_* (az_strerror()).
+ *  - one game per row: arrays are indexed [game][...]; G = num_games.
+ *  - moves are 1-based tile ids (0 = padding / "no move"), move ids are
+ *    ordinals in the ascending legal-move list, colours are 1 (X, first
+ *    player) / 2 (O), results 0 ongoing / 1 O won / 3 X won -- all as in the
+ *    reference (game/hex.py:151-179, typing/agent.py:34-41).
+ *
+ * Memory: the caller owns ONE device block of az_engine_device_bytes() bytes
+ * (allocate it with the framework's allocator, e.g. a torch uint8 tensor);
+ * az_engine_buffer() gives the offset/shape of the views the caller may read
+ * or write directly (leaf boards for the network, value/prior inputs ...).
+ */
+#ifndef AZALEA_B200_H
+#define AZALEA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZ_ABI_VERSION 1
+
+enum {
+    AZ_OK = 0,
+    AZ_E_INVALID = -1,      /* bad argument */
+    AZ_E_CUDA = -2,         /* CUDA runtime error (az_last_cuda_error()) */
+    AZ_E_NOMEM = -3,        /* device block too small */
+    AZ_E_UNSUPPORTED = -4
+};
+
+/* per-game status bits (az_status) */
+enum {
+    AZ_ST_POOL_FULL = 1,    /* physical node pool exhausted */
+    AZ_ST_TREE_FULL = 2,    /* reference MAX_NODES reached: SearchTreeFull,
+                               search_tree.py:17-22,258-259 */
+    AZ_ST_ILLEGAL = 4,      /* illegal move / inconsistent state (the
+                               reference's AssertionError, hex.py:174-176) */
+    AZ_ST_DISABLED = 8
+};
+
+/* leaf flags (leaf_info[..][1] & 0xff) */
+enum {
+    AZ_LEAF_TERMINAL_KNOWN = 1, /* re-visited terminal node, mcts.py:236-237 */
+    AZ_LEAF_TERMINAL_NEW = 2    /* first visit found the game over */
+};
+
+typedef struct az_config {
+    int32_t num_games;       /* G: games resident on this GPU */
+    int32_t board_size;      /* n: 2..19 */
+    int32_t max_batch;       /* search_batch_size upper bound, 1..32 */
+    int32_t nodes_per_game;  /* capacity of each half of a game's node pool */
+    int64_t max_nodes_ref;   /* search_tree.MAX_NODES emulation (1e7) */
+    int32_t replay_rows;     /* capacity of the replay output buffer (rows) */
+    int32_t max_plies;       /* play_game game_max_length (300) clipped to n*n */
+    uint64_t seed;           /* Philox key; streams keyed by global game id */
+    int64_t first_game_id;   /* global id of local game 0 (rank * G) */
+    int64_t game_id_stride;  /* ids of successive games in one slot differ by this
+                                (total games over all ranks) */
+} az_config;
+
+typedef struct az_engine az_engine;
+
+/* buffers the caller may view inside its device block */
+enum {
+    AZ_BUF_LEAF_BOARD = 0,  /* int8  [G][max_batch][cell_stride]  network-view cells 0/1/2 */
+    AZ_BUF_LEAF_INFO = 1,   /* int32 [G][max_batch][4] node(-1 = none), flags|colour<<8, num_moves, depth */
+    AZ_BUF_VALUE = 2,       /* f32   [G][max_batch]           evaluator output */
+    AZ_BUF_PRIOR = 3,       /* f32   [G][max_batch][n*n]      evaluator output (priors or logits) */
+    AZ_BUF_META = 4,        /* int32 [G][16] */
+    AZ_BUF_REPLAY = 5,      /* uint8 [replay_rows][replay_row_bytes] */
+    AZ_BUF_COUNTERS = 6,    /* int64 [16] engine-wide counters */
+    AZ_BUF_LEAF_MOVES = 7,  /* int32 [G][max_batch][n*n] network-view legal moves, 0-padded */
+    AZ_BUF__COUNT = 8
+};
+
+/* engine-wide counters (AZ_BUF_COUNTERS) */
+enum {
+    AZ_CNT_SIMULATIONS = 0,   /* root-to-leaf descents */
+    AZ_CNT_SUM_CHILDREN = 1,  /* sum over descents and levels of k */
+    AZ_CNT_SUM_DEPTH = 2,     /* sum over descents of depth */
+    AZ_CNT_UNIQUE_LEAVES = 3,
+    AZ_CNT_EXPANDED_CHILDREN = 4,
+    AZ_CNT_PLIES = 5,         /* committed self-play moves */
+    AZ_CNT_GAMES = 6,         /* finished self-play games */
+    AZ_CNT_REPLAY_ROWS = 7,   /* rows appended to the replay buffer */
+    AZ_CNT_REPLAY_DROPPED = 8,
+    AZ_CNT_GAMES_FAILED = 9,  /* dropped on SearchTreeFull, parallel_player.py:71-76 */
+    AZ_CNT_COMPACTED_NODES = 10,
+    AZ_CNT_NN_ROWS = 11       /* non-terminal unique leaves (rows the network must evaluate) */
+};
+
+typedef struct az_buffer_desc {
+    size_t offset;          /* bytes from the start of the device block */
+    size_t bytes;
+    int32_t elem_bytes;
+    int32_t ndim;
+    int64_t shape[4];
+} az_buffer_desc;
+
+/* -------------------------------------------------------------- lifecycle */
+
+int az_abi_version(void);
+const char *az_strerror(int code);
+const char *az_last_cuda_error(void);
+
+/* SearchTree.__init__, search_tree.py:43-57: how much device memory a pool
+ * of G trees + boards + scratch needs. */
+size_t az_engine_device_bytes(const az_config *cfg);
+int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev,
+                     size_t mem_bytes, int device);
+void az_engine_destroy(az_engine *e);
+int az_engine_buffer(const az_engine *e, int which, az_buffer_desc *out);
+int az_replay_row_bytes(const az_engine *e);
+
+/* ------------------------------------------------------------------ games */
+
+/* HexGame.reset + Policy.reset for the games whose mask byte is non-zero
+ * (NULL = all), hex.py:47-49, policy.py:72-76, search_tree.py:59-71. */
+int az_games_reset(az_engine *e, const uint8_t *mask_dev, void *stream);
+/* HexGameImpl.step on each game's root position, hex.py:172-179.  moves 0 =
+ * leave the game alone.  results_dev (nullable) receives 0/1/3. */
+int az_hex_step(az_engine *e, const int32_t *moves_dev, int32_t *results_dev,
+                void *stream);
+/* HexGame.state, hex.py:55-60: board int8[G][n*n] (0/1/2, absolute view),
+ * colour to move 0/1, result 0/1/3, ply.  Any pointer may be NULL. */
+int az_hex_state(az_engine *e, int8_t *board_dev, int32_t *color_dev,
+                 int32_t *result_dev, int32_t *ply_dev, void *stream);
+/* HexGameImpl.legal_moves, hex.py:151-159: int32[G][n*n] ascending, 0-padded */
+int az_hex_legal_moves(az_engine *e, int32_t *moves_dev, int32_t *count_dev,
+                       void *stream);
+/* Overwrite root positions (HexGame.__setstate__, hex.py:39-45): board
+ * int8[G][n*n], colour to move 1/2.  Trees are reset.  Winner is recomputed
+ * from `last_tile_dev` (nullable; -1 = none). */
+int az_hex_set_state(az_engine *e, const int8_t *board_dev,
+                     const int32_t *color_dev, const int32_t *last_tile_dev,
+                     void *stream);
+
+/* ----------------------------------------------------------------- search */
+
+typedef struct az_search_params {
+    int32_t batch_size;         /* search_batch_size, mcts.py:62 */
+    float exploration_coef;     /* c_puct, mcts.py:133 */
+    double noise_scale;         /* Dirichlet epsilon (0 = off), mcts.py:126-131 */
+    double noise_alpha;
+} az_search_params;
+
+/* evaluate_root's selection half, mcts.py:18-24: games with an unevaluated
+ * root emit the root position as leaf slot 0; others emit nothing. */
+int az_mcts_select_root(az_engine *e, void *stream);
+/* select_batch + deduplicate_leaves, mcts.py:46-76,139-152: batch_size
+ * sequential PUCT descents per game with virtual loss, undo, first-occurrence
+ * dedup, leaf position + win check, network-view board planes
+ * (mcts.py:176-181, hex.py:72-87). */
+int az_mcts_select(az_engine *e, const az_search_params *p, void *stream);
+/* Network-view legal moves of the current leaves into AZ_BUF_LEAF_MOVES
+ * (prep.batch_games + flip_player_board_moves, prep.py:15-21, hex.py:89-122);
+ * only the generic evaluator interface needs them. */
+int az_leaf_moves(az_engine *e, void *stream);
+
+enum {
+    AZ_PRIOR_PROBS = 0,     /* prior[g][b][j] by move ordinal, stride n*n */
+    AZ_PRIOR_LOGITS = 1     /* logits[g][b][tile] by network-view tile; the engine
+                               gathers legal tiles, masked log-softmax, exp
+                               (network.py:146-151, mcts.py:210) */
+};
+/* evaluate_batch's terminal rule + expand_batch + backup_batch,
+ * mcts.py:192-200,226-255.  value_dev f32[G][max_batch], prior_dev
+ * f32[G][max_batch][n*n]; NULL = the engine's own AZ_BUF_VALUE/PRIOR. */
+int az_mcts_expand_backup(az_engine *e, const float *value_dev,
+                          const float *prior_dev, int prior_kind,
+                          void *stream);
+/* evaluate_root's expansion half, mcts.py:25-26 (value discarded). */
+int az_mcts_expand_root(az_engine *e, const float *prior_dev, int prior_kind,
+                        void *stream);
+/* root.move_stats + root node, search_tree.py:105-112,192-204:
+ * visits/total_value/prior f32[G][n*n] (children in legal-move order,
+ * total_value in the stored (child's own) sign), num_children int32[G]
+ * (-1 = unevaluated root), root_nw f32[G][2] = (N, W) of the root,
+ * num_nodes int64[G] = the reference's tree.num_nodes.  NULLs are skipped. */
+int az_root_stats(az_engine *e, float *visits_dev, float *total_value_dev,
+                  float *prior_dev, int32_t *num_children_dev,
+                  float *root_nw_dev, int64_t *num_nodes_dev, void *stream);
+/* SearchTree.move, search_tree.py:115-132: re-root to child move_id (with
+ * subtree compaction) or reset when it is unevaluated; move_id -1 = skip. */
+int az_tree_move(az_engine *e, const int32_t *move_ids_dev, void *stream);
+/* per-game AZ_ST_* bits */
+int az_status(az_engine *e, int32_t *status_dev, void *stream);
+
+/* Deterministic stub evaluator on the device (TEST / BENCH aid; the same
+ * arithmetic as oracle/azalea_oracle.c:ostub_eval): fills AZ_BUF_VALUE and
+ * AZ_BUF_PRIOR (AZ_PRIOR_PROBS layout) for the current leaves. */
+int az_stub_eval(az_engine *e, int mode, void *stream);
+
+/* --------------------------------------------------------- lockstep play */
+
+typedef struct az_play_params {
+    float temperature;          /* exploration_temperature, policy.py:142-149 */
+    int32_t exploration_depth;  /* temperature 0 from this ply on */
+    int32_t move_sampling;      /* settings['move_sampling'] */
+    int32_t collect_replay;     /* play_game collect_data, play_game.py:90-96 */
+    int32_t auto_reset;         /* start a new game in a finished slot */
+} az_play_params;
+
+/* Policy.choose_action's tail + AzaleaAgent.execute_action + play_game's
+ * bookkeeping for every game at once (policy.py:160-176,
+ * azalea_agent.py:60-64, play_game.py:46-67): draw the move from the root
+ * visit distribution (device Philox stream per game), record the replay row,
+ * step the game, re-root the tree; finished games get their rewards, are
+ * flushed to the replay buffer and (auto_reset) restarted.
+ * chosen_dev (nullable) int32[G][4]: move, move_id, result, ply. */
+int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev,
+                   void *stream);
+/* Reset the replay append counter after the host has harvested the rows. */
+int az_replay_clear(az_engine *e, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZALEA_B200_H */

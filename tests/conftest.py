@@ -1,0 +1,33 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line(
+        'markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden_hex():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'hex_rules.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_formulas():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'formulas.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_mcts():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, 'mcts_traces.npz'))

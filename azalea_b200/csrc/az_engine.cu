@@ -1,0 +1,846 @@
+// az_engine.cu -- C ABI (include/azalea_b200.h) + game / lockstep-play kernels.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared
+//        -Xcompiler -fPIC   (see __graft_entry__.build()).
+// No torch, no CPU fallback: every entry point launches sm_100a kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "az_kernels.cuh"
+
+static thread_local char g_cuda_err[256] = "";
+
+static int az_check(cudaError_t err)
+{
+    if (err == cudaSuccess) return AZ_OK;
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", cudaGetErrorName(err),
+             cudaGetErrorString(err));
+    return AZ_E_CUDA;
+}
+
+static inline int az_grid(const az_engine *e)
+{
+    return (e->G + AZ_WARPS_PER_CTA - 1) / AZ_WARPS_PER_CTA;
+}
+
+#define AZ_LAUNCH(kernel, e, stream, ...)                                              \
+    do {                                                                               \
+        kernel<<<az_grid(e), AZ_WARPS_PER_CTA * 32, 0, (cudaStream_t)(stream)>>>(*(e), \
+                                                                      ##__VA_ARGS__); \
+        return az_check(cudaGetLastError());                                           \
+    } while (0)
+
+// ------------------------------------------------------------ game kernels
+
+__device__ __forceinline__ void az_game_reset(const az_engine &e, int g, int32_t *meta,
+                                              int lane, bool new_id)
+{
+    // HexGame.reset (hex.py:47-49) + Policy.reset (policy.py:72-76)
+    if (lane < e.NW) {
+        e.board[((size_t)g * 2 + 0) * e.NW + lane] = 0u;
+        e.board[((size_t)g * 2 + 1) * e.NW + lane] = 0u;
+    }
+    uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
+    az_tree_reset(nodes, meta, lane);
+    if (lane == 0) {
+        meta[M_COLOR] = 1;
+        meta[M_WINNER] = 0;
+        meta[M_PLY] = 0;
+        meta[M_STATUS] = 0;
+        meta[M_DRAW] = 0;
+        meta[M_LAST] = -1;
+        if (new_id) {
+            long long gid = ((long long)(uint32_t)meta[M_GID_LO]) | ((long long)meta[M_GID_HI] << 32);
+            gid += e.cfg.game_id_stride;
+            meta[M_GID_LO] = (int32_t)(uint32_t)(gid & 0xffffffffll);
+            meta[M_GID_HI] = (int32_t)(gid >> 32);
+            meta[M_SERIAL] += 1;
+        }
+    }
+}
+
+__global__ void k_reset(az_engine e, const uint8_t *mask, int init)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    if (mask && !mask[g]) return;
+    int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    if (init) {
+        if (lane < AZ_META_INTS) meta[lane] = 0;
+        if (lane < AZ_CNT_PER_GAME) e.counters[(size_t)g * AZ_CNT_PER_GAME + lane] = 0ull;
+        if (g == 0 && lane < 16) e.globals[lane] = 0ull;
+        __syncwarp();
+        if (lane == 0) {
+            long long gid = e.cfg.first_game_id + g;
+            meta[M_GID_LO] = (int32_t)(uint32_t)(gid & 0xffffffffll);
+            meta[M_GID_HI] = (int32_t)(gid >> 32);
+        }
+        __syncwarp();
+    }
+    az_game_reset(e, g, meta, lane, false);
+}
+
+// HexGameImpl.step on the root position (hex.py:172-179)
+__device__ __forceinline__ int az_root_step(const az_engine &e, int g, int32_t *meta,
+                                            int tile, int lane)
+{
+    uint32_t *bx = e.board + ((size_t)g * 2 + 0) * e.NW;
+    uint32_t *bo = e.board + ((size_t)g * 2 + 1) * e.NW;
+    uint32_t x = lane < e.NW ? bx[lane] : 0u, o = lane < e.NW ? bo[lane] : 0u;
+    const int color = meta[M_COLOR];
+    const uint32_t bit = 1u << (tile & 31);
+    const bool taken = __any_sync(AZ_FULL, lane == (tile >> 5) && ((x | o) & bit));
+    if (tile < 0 || tile >= e.nn || taken || meta[M_WINNER] != 0) {
+        if (lane == 0) meta[M_STATUS] |= AZ_ST_ILLEGAL;     // hex.py:174-176
+        return -1;
+    }
+    if (lane == (tile >> 5)) {
+        if (color == 1) { x |= bit; bx[lane] = x; } else { o |= bit; bo[lane] = o; }
+    }
+    const bool won = az_hex_wins(color == 1 ? x : o, e.n, e.div_magic, tile, color);
+    if (lane == 0) {
+        meta[M_COLOR] = 3 - color;
+        meta[M_WINNER] = won ? color : 0;
+        meta[M_PLY] += 1;
+        meta[M_LAST] = tile;
+    }
+    return won ? color : 0;
+}
+
+__global__ void k_hex_step(az_engine e, const int32_t *moves, int32_t *results)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    const int move = moves[g];
+    int winner = meta[M_WINNER];
+    if (move != 0) {
+        int w = az_root_step(e, g, meta, move - 1, lane);
+        if (w >= 0) winner = w;
+    }
+    // HexGameImpl.result, hex.py:161-170
+    if (results && lane == 0) results[g] = winner == 0 ? 0 : (winner == 2 ? 1 : 3);
+}
+
+__global__ void k_hex_state(az_engine e, int8_t *board, int32_t *color, int32_t *result,
+                            int32_t *ply)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    if (board) {
+        const uint32_t *bx = e.board + ((size_t)g * 2 + 0) * e.NW;
+        const uint32_t *bo = e.board + ((size_t)g * 2 + 1) * e.NW;
+        for (int t = lane; t < e.nn; t += 32) {
+            uint32_t x = (bx[t >> 5] >> (t & 31)) & 1u, o = (bo[t >> 5] >> (t & 31)) & 1u;
+            board[(size_t)g * e.nn + t] = (int8_t)(x + 2u * o);
+        }
+    }
+    if (lane == 0) {
+        const int w = meta[M_WINNER];
+        if (color) color[g] = meta[M_COLOR] - 1;
+        if (result) result[g] = meta[M_DRAW] ? 2 : (w == 0 ? 0 : (w == 2 ? 1 : 3));
+        if (ply) ply[g] = meta[M_PLY];
+    }
+}
+
+__global__ void k_hex_legal(az_engine e, int32_t *moves, int32_t *count)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    const uint32_t valid = az_valid_word(lane, e.nn);
+    uint32_t occ = lane < e.NW
+        ? (e.board[((size_t)g * 2 + 0) * e.NW + lane] | e.board[((size_t)g * 2 + 1) * e.NW + lane]) : ~0u;
+    // hex.py:152-153: no legal moves once the game is won
+    uint32_t emp = meta[M_WINNER] ? 0u : (~occ & valid);
+    int base = 0;
+    int32_t *row = moves + (size_t)g * e.nn;
+    for (int s = 0; s < e.NW; s++) {
+        uint32_t es = __shfl_sync(AZ_FULL, emp, s);
+        if ((es >> lane) & 1u)
+            row[base + __popc(es & ((1u << lane) - 1u))] = 32 * s + lane + 1;
+        base += __popc(es);
+    }
+    for (int j = base + lane; j < e.nn; j += 32) row[j] = 0;
+    if (count && lane == 0) count[g] = base;
+}
+
+__global__ void k_hex_set_state(az_engine e, const int8_t *board, const int32_t *color,
+                                const int32_t *last_tile, int reset_trees)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    uint32_t x = 0, o = 0;
+    for (int s = 0; s < e.NW; s++) {
+        int t = 32 * s + lane;
+        int8_t c = t < e.nn ? board[(size_t)g * e.nn + t] : 0;
+        uint32_t wx = __ballot_sync(AZ_FULL, c == 1), wo = __ballot_sync(AZ_FULL, c == 2);
+        if (lane == s) { x = wx; o = wo; }
+    }
+    if (lane < e.NW) {
+        e.board[((size_t)g * 2 + 0) * e.NW + lane] = x;
+        e.board[((size_t)g * 2 + 1) * e.NW + lane] = o;
+    }
+    const int ply = az_count_bits(x | o);
+    if (reset_trees) {
+        uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
+        az_tree_reset(nodes, meta, lane);
+    }
+    int winner = 0;
+    const int lt = last_tile ? last_tile[g] : -1;
+    if (lt >= 0 && lt < e.nn) {
+        const bool isx = __any_sync(AZ_FULL, lane == (lt >> 5) && ((x >> (lt & 31)) & 1u));
+        const bool iso = __any_sync(AZ_FULL, lane == (lt >> 5) && ((o >> (lt & 31)) & 1u));
+        if (isx && az_hex_wins(x, e.n, e.div_magic, lt, 1)) winner = 1;
+        if (iso && az_hex_wins(o, e.n, e.div_magic, lt, 2)) winner = 2;
+    }
+    if (lane == 0) {
+        meta[M_COLOR] = color[g];
+        meta[M_WINNER] = winner;
+        meta[M_PLY] = ply;
+        meta[M_STATUS] = 0;
+        meta[M_DRAW] = 0;
+        meta[M_LAST] = lt;
+    }
+}
+
+// network-view legal moves of the current leaves (prep.py:15-21 padding,
+// hex.py:105-121 flip): original ascending tile order, flipped coordinates
+__global__ void k_leaf_moves(az_engine e)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const uint32_t valid = az_valid_word(lane, e.nn);
+    for (int b = 0; b < e.B; b++) {
+        const int4 inf = e.leaf_info[(size_t)g * e.B + b];
+        int32_t *row = e.leaf_moves + ((size_t)g * e.B + b) * e.nn;
+        int base = 0;
+        if (inf.x >= 0 && (inf.y & 0xff) == 0) {
+            const uint32_t *lm = e.leaf_masks + ((size_t)g * e.B + b) * 2 * e.NW;
+            const int flip = (inf.y >> 8) & 1;
+            uint32_t emp = lane < e.NW ? (~(lm[lane] | lm[e.NW + lane]) & valid) : 0u;
+            for (int s = 0; s < e.NW; s++) {
+                uint32_t es = __shfl_sync(AZ_FULL, emp, s);
+                if ((es >> lane) & 1u) {
+                    int t = 32 * s + lane;
+                    row[base + __popc(es & ((1u << lane) - 1u))] =
+                        (flip ? az_flip_tile(t, e.n, e.div_magic) : t) + 1;
+                }
+                base += __popc(es);
+            }
+        }
+        for (int j = base + lane; j < e.nn; j += 32) row[j] = 0;
+    }
+}
+
+__global__ void k_root_stats(az_engine e, float *visits, float *total_value, float *prior,
+                             int32_t *num_children, float *root_nw, int64_t *num_nodes)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    const uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
+    const uint4 root = nodes[0];
+    int k = -1, fc = 0;
+    if (root.w != AZ_UNEVAL) { k = (int)(root.w & AZ_LINK_KMASK); fc = (int)(root.w >> AZ_LINK_KBITS); }
+    for (int j = lane; j < e.nn; j += 32) {
+        uint4 r = j < k ? nodes[fc + j] : make_uint4(0, 0, 0, 0);
+        if (visits) visits[(size_t)g * e.nn + j] = __uint_as_float(r.x);
+        if (total_value) total_value[(size_t)g * e.nn + j] = __uint_as_float(r.y);
+        if (prior) prior[(size_t)g * e.nn + j] = __uint_as_float(r.z);
+    }
+    if (lane == 0) {
+        if (num_children) num_children[g] = k;
+        if (root_nw) {
+            root_nw[2 * g] = __uint_as_float(root.x);
+            root_nw[2 * g + 1] = __uint_as_float(root.y);
+        }
+        if (num_nodes)
+            num_nodes[g] = ((long long)(uint32_t)meta[M_VREF_LO]) | ((long long)meta[M_VREF_HI] << 32);
+    }
+}
+
+__global__ void k_tree_move(az_engine e, const int32_t *move_ids)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int mv = move_ids[g];
+    if (mv < 0) return;
+    az_reroot(e, g, e.meta + (size_t)g * AZ_META_INTS, mv, lane);
+}
+
+__global__ void k_status(az_engine e, int32_t *status)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < e.G) status[g] = e.meta[(size_t)g * AZ_META_INTS + M_STATUS];
+}
+
+// Deterministic stub evaluator (test / bench aid): same arithmetic as
+// oracle/azalea_oracle.c:ostub_eval, on the network view of each leaf.
+__global__ void k_stub_eval(az_engine e, int mode)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const uint32_t valid = az_valid_word(lane, e.nn);
+    for (int b = 0; b < e.B; b++) {
+        const int4 inf = e.leaf_info[(size_t)g * e.B + b];
+        if (inf.x < 0 || (inf.y & 0xff) != 0) continue;
+        const uint32_t *lm = e.leaf_masks + ((size_t)g * e.B + b) * 2 * e.NW;
+        const int flip = (inf.y >> 8) & 1;
+        const uint32_t x = lane < e.NW ? lm[lane] : 0u, o = lane < e.NW ? lm[e.NW + lane] : 0u;
+        // board hash: sum over stones of fmix32((2*view_tile + view_colour) * K)
+        uint32_t part = 0;
+        for (int s = 0; s < e.NW; s++) {
+            uint32_t xs = __shfl_sync(AZ_FULL, x, s), os = __shfl_sync(AZ_FULL, o, s);
+            int t = 32 * s + lane;
+            uint32_t c = ((xs >> lane) & 1u) + 2u * ((os >> lane) & 1u);
+            if (c) {
+                uint32_t vt = flip ? (uint32_t)az_flip_tile(t, e.n, e.div_magic) : (uint32_t)t;
+                uint32_t vc = flip ? 3u - c : c;
+                part += az_fmix32((2u * vt + vc) * 0x9E3779B1u);
+            }
+        }
+        const uint32_t h0 = az_fmix32(__reduce_add_sync(AZ_FULL, part) ^ (uint32_t)e.n);
+        float value;
+        if (mode == 0) value = 0.0f;
+        else if (mode == 1) value = __fdiv_rn((float)((int)((h0 >> 8) % 17u) - 8), 8.0f);
+        else value = __fadd_rn(__fmul_rn((float)(h0 >> 8), 1.0f / 8388608.0f), -1.0f);
+        const size_t row = (size_t)g * e.B + b;
+        if (lane == 0) e.value[row] = value;
+        // weights by ordinal, prior = w / sum(w) with one IEEE division
+        const uint32_t emp = ~(x | o) & valid;
+        uint32_t wsum = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            int base = 0;
+            uint32_t wpart = 0;
+            for (int s = 0; s < e.NW; s++) {
+                uint32_t es = __shfl_sync(AZ_FULL, emp, s);
+                if ((es >> lane) & 1u) {
+                    int t = 32 * s + lane;
+                    uint32_t vt = flip ? (uint32_t)az_flip_tile(t, e.n, e.div_magic) : (uint32_t)t;
+                    uint32_t hj = az_fmix32(h0 ^ (vt * 0x9E3779B1u + 0x7F4A7C15u));
+                    uint32_t w = mode == 0 ? 1u : (mode == 1 ? 1u + (hj >> 28) : 1u + (hj >> 24));
+                    if (pass == 0) wpart += w;
+                    else e.prior[row * e.nn + base + __popc(es & ((1u << lane) - 1u))] =
+                             __fdiv_rn((float)w, (float)wsum);
+                }
+                base += __popc(es);
+            }
+            if (pass == 0) wsum = __reduce_add_sync(AZ_FULL, wpart);
+        }
+    }
+}
+
+// ------------------------------------------------------------ lockstep play
+
+__global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32)
+k_play_commit(az_engine e, az_play_params p, int32_t *chosen)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    unsigned long long *cnt = e.counters + (size_t)g * AZ_CNT_PER_GAME;
+    const int status = meta[M_STATUS];
+    const int ply = meta[M_PLY];
+    if (status & AZ_ST_DISABLED) return;
+    if (status & AZ_ST_ILLEGAL) return;     // a bug, not a game outcome: keep it visible
+    if (status != 0) {
+        // SearchTreeFull: the reference drops the game and starts another
+        // (parallel_player.py:71-76)
+        if (lane == 0) {
+            cnt[AZ_CNT_GAMES_FAILED] += 1;
+            if (chosen) reinterpret_cast<int4 *>(chosen)[g] = make_int4(0, -1, -1, ply);
+        }
+        __syncwarp();
+        if (p.auto_reset) az_game_reset(e, g, meta, lane, true);
+        return;
+    }
+    if (meta[M_WINNER] != 0 || meta[M_DRAW] != 0) {
+        if (chosen && lane == 0) reinterpret_cast<int4 *>(chosen)[g] = make_int4(0, -1, -1, ply);
+        return;
+    }
+    uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
+    const uint32_t rootlink = nodes[0].w;
+    if (rootlink == AZ_UNEVAL || (rootlink & AZ_LINK_KMASK) == 0u) {
+        if (lane == 0) meta[M_STATUS] = status | AZ_ST_ILLEGAL;
+        return;
+    }
+    const int k = (int)(rootlink & AZ_LINK_KMASK), fc = (int)(rootlink >> AZ_LINK_KBITS);
+    const int nslots = (k + 31) >> 5;
+    // Policy.choose_action, policy.py:142-149
+    float temp = 0.0f;
+    if (p.move_sampling && ply < p.exploration_depth) temp = p.temperature;
+    const uint2 key = make_uint2((uint32_t)e.cfg.seed ^ (uint32_t)meta[M_GID_LO],
+                                 (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
+    const uint4 rnd = az_philox(make_uint4(0u, 0u, (uint32_t)ply, 0xC0111700u), key);
+
+    // as_distribution + multinomial (search_tree.py:327-344, policy.py:160):
+    // temperature 0 = uniform over the arg-max ties, otherwise p ~ N^(1/T)
+    int move_id = 0;
+    if (temp == 0.0f) {
+        int mx = 0;
+        for (int s = 0; s < nslots; s++) {
+            int j = lane + 32 * s;
+            int nv = j < k ? (int)__uint_as_float(nodes[fc + j].x) : -1;
+            mx = max(mx, __reduce_max_sync(AZ_FULL, nv));
+        }
+        int ties = 0;
+        for (int s = 0; s < nslots; s++) {
+            int j = lane + 32 * s;
+            bool hit = j < k && (int)__uint_as_float(nodes[fc + j].x) == mx;
+            ties += __popc(__ballot_sync(AZ_FULL, hit));
+        }
+        int pick = (int)(rnd.x % (uint32_t)ties);
+        for (int s = 0; s < nslots; s++) {
+            int j = lane + 32 * s;
+            bool hit = j < k && (int)__uint_as_float(nodes[fc + j].x) == mx;
+            uint32_t ball = __ballot_sync(AZ_FULL, hit);
+            int c = __popc(ball);
+            if (pick < c) { move_id = 32 * s + az_nth_set_bit(ball, pick); break; }
+            pick -= c;
+        }
+    } else {
+        double tot = 0.0;
+        const double inv_t = 1.0 / (double)temp;
+        for (int s = 0; s < nslots; s++) {
+            int j = lane + 32 * s;
+            double w = 0.0;
+            if (j < k) {
+                float nv = __uint_as_float(nodes[fc + j].x);
+                w = temp == 1.0f ? (double)nv : (nv > 0.0f ? pow((double)nv, inv_t) : 0.0);
+            }
+            for (int off = 16; off; off >>= 1) w += __shfl_xor_sync(AZ_FULL, w, off);
+            tot += w;
+        }
+        const double target = tot * (((double)rnd.x + 0.5) * (1.0 / 4294967296.0));
+        double acc = 0.0;
+        move_id = -1;
+        for (int s = 0; s < nslots && move_id < 0; s++) {
+            int j = lane + 32 * s;
+            double w = 0.0;
+            if (j < k) {
+                float nv = __uint_as_float(nodes[fc + j].x);
+                w = temp == 1.0f ? (double)nv : (nv > 0.0f ? pow((double)nv, inv_t) : 0.0);
+            }
+            double incl = w;
+            for (int off = 1; off < 32; off <<= 1) {
+                double t = __shfl_up_sync(AZ_FULL, incl, off);
+                if (lane >= off) incl += t;
+            }
+            uint32_t ball = __ballot_sync(AZ_FULL, w > 0.0 && acc + incl > target);
+            if (ball) move_id = 32 * s + __ffs(ball) - 1;
+            acc += __shfl_sync(AZ_FULL, incl, 31);
+        }
+        if (move_id < 0) {
+            // rounding left target == total: take the last visited child
+            for (int s = nslots - 1; s >= 0 && move_id < 0; s--) {
+                int j = lane + 32 * s;
+                bool hit = j < k && __uint_as_float(nodes[fc + j].x) > 0.0f;
+                uint32_t ball = __ballot_sync(AZ_FULL, hit);
+                if (ball) move_id = 32 * s + 31 - __clz(ball);
+            }
+            if (move_id < 0) move_id = 0;
+        }
+    }
+
+    const uint32_t valid = az_valid_word(lane, e.nn);
+    const uint32_t x = lane < e.NW ? e.board[((size_t)g * 2 + 0) * e.NW + lane] : 0u;
+    const uint32_t o = lane < e.NW ? e.board[((size_t)g * 2 + 1) * e.NW + lane] : 0u;
+    const int tile = az_kth_empty(~(x | o) & valid, move_id, e.NW);
+    const int color = meta[M_COLOR];
+
+    // replay row before the move (play_game.py:90-96)
+    if (p.collect_replay && ply < e.hist_rows) {
+        uint8_t *row = e.hist + ((size_t)g * e.hist_rows + ply) * e.row_bytes;
+        if (lane == 0) {
+            az_row_header h;
+            h.game_id = ((long long)(uint32_t)meta[M_GID_LO]) | ((long long)meta[M_GID_HI] << 32);
+            h.ply = ply;
+            h.color = color - 1;
+            h.num_moves = k;
+            h.reward = 0.0f;
+            h.result = 0;
+            h.temperature = temp;
+            h.move = tile + 1;
+            h.move_id = move_id;
+            h.game_len = 0;
+            h.reserved = 0;
+            *reinterpret_cast<az_row_header *>(row) = h;
+        }
+        int8_t *cells = reinterpret_cast<int8_t *>(row + sizeof(az_row_header));
+        for (int s = 0; s < e.NW; s++) {
+            uint32_t xs = __shfl_sync(AZ_FULL, x, s), os = __shfl_sync(AZ_FULL, o, s);
+            int t = 32 * s + lane;
+            if (t < e.cell_stride) cells[t] = (int8_t)(((xs >> lane) & 1u) + 2u * ((os >> lane) & 1u));
+        }
+        float *vis = reinterpret_cast<float *>(row + sizeof(az_row_header) + e.cell_stride);
+        for (int j = lane; j < e.nn; j += 32)
+            vis[j] = j < k ? __uint_as_float(nodes[fc + j].x) : 0.0f;
+    }
+    __syncwarp();
+
+    // AzaleaAgent.execute_action, azalea_agent.py:60-64: tree first, then game
+    az_reroot(e, g, meta, move_id, lane);
+    __syncwarp();
+    const int won = az_root_step(e, g, meta, tile, lane);
+    __syncwarp();
+    const int nply = ply + 1;
+    int result = won > 0 ? (won == 2 ? 1 : 3) : 0;
+    bool over = won > 0;
+    if (!over && nply >= e.cfg.max_plies) {
+        // play_game.py:57-61: no winner within game_max_length -> draw
+        over = true;
+        result = 2;
+        if (lane == 0) meta[M_DRAW] = 1;
+    }
+    if (lane == 0) {
+        cnt[AZ_CNT_PLIES] += 1;
+        if (chosen) reinterpret_cast<int4 *>(chosen)[g] = make_int4(tile + 1, move_id, result, nply);
+    }
+    if (!over) return;
+
+    // play_game.py:63-67: reward = result - 2 for the first player's rows,
+    // negated on the second player's
+    if (p.collect_replay) {
+        const int rows = min(nply, e.hist_rows);
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&e.globals[0], (unsigned long long)rows);
+        base = __shfl_sync(AZ_FULL, base, 0);
+        if (base + rows <= (unsigned long long)e.cfg.replay_rows) {
+            const uint8_t *src = e.hist + (size_t)g * e.hist_rows * e.row_bytes;
+            uint8_t *dst = e.replay + (size_t)base * e.row_bytes;
+            const size_t n16 = (size_t)rows * e.row_bytes / 16;
+            for (size_t i = lane; i < n16; i += 32)
+                reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32) {
+                az_row_header *h = reinterpret_cast<az_row_header *>(dst + (size_t)r * e.row_bytes);
+                float rw = (float)(result - 2);
+                h->reward = (r & 1) ? -rw : rw;
+                h->result = result;
+                h->game_len = nply;
+            }
+            if (lane == 0) cnt[AZ_CNT_REPLAY_ROWS] += rows;
+        } else if (lane == 0) {
+            atomicAdd(&e.globals[0], (unsigned long long)(-(long long)rows));
+            cnt[AZ_CNT_REPLAY_DROPPED] += rows;
+        }
+    }
+    if (lane == 0) cnt[AZ_CNT_GAMES] += 1;
+    __syncwarp();
+    if (p.auto_reset) az_game_reset(e, g, meta, lane, true);
+}
+
+__global__ void k_replay_clear(az_engine e)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) e.globals[0] = 0ull;
+}
+
+// =================================================================== C ABI
+
+static size_t az_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int az_layout(az_engine *e, const az_config *cfg)
+{
+    if (!cfg || cfg->num_games < 1 || cfg->board_size < 2 || cfg->board_size > 19 ||
+        cfg->max_batch < 1 || cfg->max_batch > 32 || cfg->nodes_per_game < 2 ||
+        cfg->nodes_per_game > AZ_MAX_NODE || cfg->replay_rows < 0)
+        return AZ_E_INVALID;
+    memset(e, 0, sizeof(*e));
+    e->cfg = *cfg;
+    e->G = cfg->num_games;
+    e->n = cfg->board_size;
+    e->nn = e->n * e->n;
+    e->NW = (e->nn + 31) / 32;
+    e->B = cfg->max_batch;
+    e->C = cfg->nodes_per_game;
+    e->cell_stride = (e->nn + 15) & ~15;
+    e->path_stride = (e->nn + 3) & ~3;
+    e->row_bytes = (int)((sizeof(az_row_header) + e->cell_stride + 4 * (size_t)e->nn + 15) & ~(size_t)15);
+    e->hist_rows = cfg->max_plies > 0 && cfg->max_plies < e->nn ? cfg->max_plies : e->nn;
+    if (e->cfg.max_plies <= 0) e->cfg.max_plies = 300;
+    if (e->cfg.max_nodes_ref <= 0) e->cfg.max_nodes_ref = 10000000;
+    if (e->cfg.game_id_stride <= 0) e->cfg.game_id_stride = e->G;
+    if (cfg->replay_rows == 0) e->hist_rows = 0;
+    e->div_magic = 65536u / (uint32_t)e->n + 1u;
+    size_t off = 0;
+    size_t o_nodes = off; off = az_align(off + (size_t)e->G * 2 * e->C * sizeof(uint4));
+    size_t o_board = off; off = az_align(off + (size_t)e->G * 2 * e->NW * 4);
+    size_t o_meta = off; off = az_align(off + (size_t)e->G * AZ_META_INTS * 4);
+    size_t o_path = off; off = az_align(off + (size_t)e->G * e->B * e->path_stride * 4);
+    size_t o_info = off; off = az_align(off + (size_t)e->G * e->B * sizeof(int4));
+    size_t o_lmask = off; off = az_align(off + (size_t)e->G * e->B * 2 * e->NW * 4);
+    size_t o_lboard = off; off = az_align(off + (size_t)e->G * e->B * e->cell_stride);
+    size_t o_lmoves = off; off = az_align(off + (size_t)e->G * e->B * e->nn * 4);
+    size_t o_value = off; off = az_align(off + (size_t)e->G * e->B * 4);
+    size_t o_prior = off; off = az_align(off + (size_t)e->G * e->B * e->nn * 4);
+    size_t o_cnt = off; off = az_align(off + (size_t)e->G * AZ_CNT_PER_GAME * 8);
+    size_t o_glob = off; off = az_align(off + 16 * 8);
+    size_t o_hist = off; off = az_align(off + (size_t)e->G * e->hist_rows * e->row_bytes);
+    size_t o_replay = off; off = az_align(off + (size_t)e->cfg.replay_rows * e->row_bytes);
+    e->total_bytes = off;
+    // offsets are stored as pointers relative to NULL until create() binds them
+    e->nodes = (uint4 *)o_nodes;
+    e->board = (uint32_t *)o_board;
+    e->meta = (int32_t *)o_meta;
+    e->path = (uint32_t *)o_path;
+    e->leaf_info = (int4 *)o_info;
+    e->leaf_masks = (uint32_t *)o_lmask;
+    e->leaf_board = (int8_t *)o_lboard;
+    e->leaf_moves = (int32_t *)o_lmoves;
+    e->value = (float *)o_value;
+    e->prior = (float *)o_prior;
+    e->counters = (unsigned long long *)o_cnt;
+    e->globals = (unsigned long long *)o_glob;
+    e->hist = (uint8_t *)o_hist;
+    e->replay = (uint8_t *)o_replay;
+#define AZ_DESC(which, off_, bytes_, elem_, nd_, s0, s1, s2, s3)                         \
+    do {                                                                                 \
+        az_buffer_desc *d = &e->desc[which];                                             \
+        d->offset = off_; d->bytes = bytes_; d->elem_bytes = elem_; d->ndim = nd_;       \
+        d->shape[0] = s0; d->shape[1] = s1; d->shape[2] = s2; d->shape[3] = s3;          \
+    } while (0)
+    AZ_DESC(AZ_BUF_LEAF_BOARD, o_lboard, (size_t)e->G * e->B * e->cell_stride, 1, 3, e->G, e->B, e->cell_stride, 0);
+    AZ_DESC(AZ_BUF_LEAF_INFO, o_info, (size_t)e->G * e->B * 16, 4, 3, e->G, e->B, 4, 0);
+    AZ_DESC(AZ_BUF_VALUE, o_value, (size_t)e->G * e->B * 4, 4, 2, e->G, e->B, 0, 0);
+    AZ_DESC(AZ_BUF_PRIOR, o_prior, (size_t)e->G * e->B * e->nn * 4, 4, 3, e->G, e->B, e->nn, 0);
+    AZ_DESC(AZ_BUF_META, o_meta, (size_t)e->G * AZ_META_INTS * 4, 4, 2, e->G, AZ_META_INTS, 0, 0);
+    AZ_DESC(AZ_BUF_REPLAY, o_replay, (size_t)e->cfg.replay_rows * e->row_bytes, 1, 2, e->cfg.replay_rows, e->row_bytes, 0, 0);
+    AZ_DESC(AZ_BUF_COUNTERS, o_cnt, (size_t)e->G * AZ_CNT_PER_GAME * 8, 8, 2, e->G, AZ_CNT_PER_GAME, 0, 0);
+    AZ_DESC(AZ_BUF_LEAF_MOVES, o_lmoves, (size_t)e->G * e->B * e->nn * 4, 4, 3, e->G, e->B, e->nn, 0);
+    AZ_DESC(AZ_BUF_GLOBALS, o_glob, 16 * 8, 8, 1, 16, 0, 0, 0);
+#undef AZ_DESC
+    return AZ_OK;
+}
+
+extern "C" {
+
+int az_abi_version(void) { return AZ_ABI_VERSION; }
+
+const char *az_strerror(int code)
+{
+    switch (code) {
+    case AZ_OK: return "ok";
+    case AZ_E_INVALID: return "invalid argument";
+    case AZ_E_CUDA: return "CUDA error";
+    case AZ_E_NOMEM: return "device block too small";
+    case AZ_E_UNSUPPORTED: return "unsupported";
+    default: return "unknown error";
+    }
+}
+
+const char *az_last_cuda_error(void) { return g_cuda_err; }
+
+size_t az_engine_device_bytes(const az_config *cfg)
+{
+    az_engine tmp;
+    if (az_layout(&tmp, cfg) != AZ_OK) return 0;
+    return tmp.total_bytes;
+}
+
+int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_t mem_bytes,
+                     int device)
+{
+    if (!out || !mem_dev) return AZ_E_INVALID;
+    az_engine *e = (az_engine *)calloc(1, sizeof(az_engine));
+    if (!e) return AZ_E_INVALID;
+    int rc = az_layout(e, cfg);
+    if (rc != AZ_OK) { free(e); return rc; }
+    if (mem_bytes < e->total_bytes) { free(e); return AZ_E_NOMEM; }
+    if (((uintptr_t)mem_dev & 255) != 0) { free(e); return AZ_E_INVALID; }
+    rc = az_check(cudaSetDevice(device));
+    if (rc != AZ_OK) { free(e); return rc; }
+    e->device = device;
+    char *base = (char *)mem_dev;
+#define AZ_BIND(field, type) e->field = (type)(base + (size_t)e->field)
+    AZ_BIND(nodes, uint4 *);
+    AZ_BIND(board, uint32_t *);
+    AZ_BIND(meta, int32_t *);
+    AZ_BIND(path, uint32_t *);
+    AZ_BIND(leaf_info, int4 *);
+    AZ_BIND(leaf_masks, uint32_t *);
+    AZ_BIND(leaf_board, int8_t *);
+    AZ_BIND(leaf_moves, int32_t *);
+    AZ_BIND(value, float *);
+    AZ_BIND(prior, float *);
+    AZ_BIND(counters, unsigned long long *);
+    AZ_BIND(globals, unsigned long long *);
+    AZ_BIND(hist, uint8_t *);
+    AZ_BIND(replay, uint8_t *);
+#undef AZ_BIND
+    // scratch the evaluator reads even for unused slots must be defined
+    rc = az_check(cudaMemsetAsync(e->leaf_board, 0, (size_t)e->G * e->B * e->cell_stride, 0));
+    if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->meta, 0, (size_t)e->G * AZ_META_INTS * 4, 0));
+    if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->value, 0, (size_t)e->G * e->B * 4, 0));
+    if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->prior, 0, (size_t)e->G * e->B * e->nn * 4, 0));
+    if (rc == AZ_OK) {
+        k_reset<<<az_grid(e), AZ_WARPS_PER_CTA * 32, 0, 0>>>(*e, NULL, 1);
+        rc = az_check(cudaGetLastError());
+    }
+    if (rc == AZ_OK) rc = az_check(cudaStreamSynchronize(0));
+    if (rc != AZ_OK) { free(e); return rc; }
+    *out = e;
+    return AZ_OK;
+}
+
+void az_engine_destroy(az_engine *e) { free(e); }
+
+int az_engine_buffer(const az_engine *e, int which, az_buffer_desc *out)
+{
+    if (!e || !out || which < 0 || which >= AZ_BUF__COUNT) return AZ_E_INVALID;
+    *out = e->desc[which];
+    return AZ_OK;
+}
+
+int az_replay_row_bytes(const az_engine *e) { return e ? e->row_bytes : AZ_E_INVALID; }
+
+int az_games_reset(az_engine *e, const uint8_t *mask_dev, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    AZ_LAUNCH(k_reset, e, stream, mask_dev, 0);
+}
+
+int az_hex_step(az_engine *e, const int32_t *moves_dev, int32_t *results_dev, void *stream)
+{
+    if (!e || !moves_dev) return AZ_E_INVALID;
+    AZ_LAUNCH(k_hex_step, e, stream, moves_dev, results_dev);
+}
+
+int az_hex_state(az_engine *e, int8_t *board_dev, int32_t *color_dev, int32_t *result_dev,
+                 int32_t *ply_dev, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    AZ_LAUNCH(k_hex_state, e, stream, board_dev, color_dev, result_dev, ply_dev);
+}
+
+int az_hex_legal_moves(az_engine *e, int32_t *moves_dev, int32_t *count_dev, void *stream)
+{
+    if (!e || !moves_dev) return AZ_E_INVALID;
+    AZ_LAUNCH(k_hex_legal, e, stream, moves_dev, count_dev);
+}
+
+int az_hex_set_state(az_engine *e, const int8_t *board_dev, const int32_t *color_dev,
+                     const int32_t *last_tile_dev, int reset_trees, void *stream)
+{
+    if (!e || !board_dev || !color_dev) return AZ_E_INVALID;
+    AZ_LAUNCH(k_hex_set_state, e, stream, board_dev, color_dev, last_tile_dev, reset_trees);
+}
+
+static int az_select_launch(az_engine *e, const az_select_args &a, void *stream)
+{
+    if (e->NW <= 4) {
+        AZ_LAUNCH(k_select<4>, e, stream, a);
+    } else {
+        AZ_LAUNCH(k_select<12>, e, stream, a);
+    }
+}
+
+int az_mcts_select_root(az_engine *e, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    az_select_args a;
+    a.batch = 1; a.coef = 0.0f; a.noise_scale = 0.0; a.noise_alpha = 1.0; a.root_mode = 1;
+    return az_select_launch(e, a, stream);
+}
+
+int az_mcts_select(az_engine *e, const az_search_params *p, void *stream)
+{
+    if (!e || !p || p->batch_size < 1 || p->batch_size > e->B) return AZ_E_INVALID;
+    az_select_args a;
+    a.batch = p->batch_size; a.coef = p->exploration_coef;
+    a.noise_scale = p->noise_scale; a.noise_alpha = p->noise_alpha; a.root_mode = 0;
+    return az_select_launch(e, a, stream);
+}
+
+int az_leaf_moves(az_engine *e, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    AZ_LAUNCH(k_leaf_moves, e, stream);
+}
+
+static int az_expand_launch(az_engine *e, const float *value_dev, const float *prior_dev,
+                            int prior_kind, int root_mode, void *stream)
+{
+    if (!e || (prior_kind != AZ_PRIOR_PROBS && prior_kind != AZ_PRIOR_LOGITS)) return AZ_E_INVALID;
+    az_expand_args a;
+    a.batch = root_mode ? 1 : e->B;
+    a.prior_kind = prior_kind;
+    a.value = value_dev ? value_dev : e->value;
+    a.prior = prior_dev ? prior_dev : e->prior;
+    a.root_mode = root_mode;
+    if (e->NW <= 4) {
+        AZ_LAUNCH(k_expand_backup<4>, e, stream, a);
+    } else {
+        AZ_LAUNCH(k_expand_backup<12>, e, stream, a);
+    }
+}
+
+int az_mcts_expand_backup(az_engine *e, const float *value_dev, const float *prior_dev,
+                          int prior_kind, void *stream)
+{
+    return az_expand_launch(e, value_dev, prior_dev, prior_kind, 0, stream);
+}
+
+int az_mcts_expand_root(az_engine *e, const float *prior_dev, int prior_kind, void *stream)
+{
+    return az_expand_launch(e, NULL, prior_dev, prior_kind, 1, stream);
+}
+
+int az_root_stats(az_engine *e, float *visits_dev, float *total_value_dev, float *prior_dev,
+                  int32_t *num_children_dev, float *root_nw_dev, int64_t *num_nodes_dev,
+                  void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    AZ_LAUNCH(k_root_stats, e, stream, visits_dev, total_value_dev, prior_dev, num_children_dev,
+              root_nw_dev, num_nodes_dev);
+}
+
+int az_tree_move(az_engine *e, const int32_t *move_ids_dev, void *stream)
+{
+    if (!e || !move_ids_dev) return AZ_E_INVALID;
+    AZ_LAUNCH(k_tree_move, e, stream, move_ids_dev);
+}
+
+int az_status(az_engine *e, int32_t *status_dev, void *stream)
+{
+    if (!e || !status_dev) return AZ_E_INVALID;
+    k_status<<<(e->G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*e, status_dev);
+    return az_check(cudaGetLastError());
+}
+
+int az_stub_eval(az_engine *e, int mode, void *stream)
+{
+    if (!e || mode < 0 || mode > 2) return AZ_E_INVALID;
+    AZ_LAUNCH(k_stub_eval, e, stream, mode);
+}
+
+int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)
+{
+    if (!e || !p) return AZ_E_INVALID;
+    if (p->collect_replay && e->hist_rows == 0) return AZ_E_INVALID;
+    AZ_LAUNCH(k_play_commit, e, stream, *p, chosen_dev);
+}
+
+int az_replay_clear(az_engine *e, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    k_replay_clear<<<1, 32, 0, (cudaStream_t)stream>>>(*e);
+    return az_check(cudaGetLastError());
+}
+
+} // extern "C"

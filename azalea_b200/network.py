@@ -1,0 +1,180 @@
+"""The evaluator: 6x64 residual tower with value and policy heads.
+
+Same architecture, parameter names and ``run`` contract as the reference's
+``HexNetwork`` (azalea/network.py:17-152), so reference checkpoints load and
+this module can be dropped into the reference's ``Policy``.  Two ways in:
+
+* ``forward`` / ``run``: the reference's interface (int32 boards + padded
+  legal-move lists -> value, moves_logprob), in the module's own dtype.
+* ``evaluate_cells``: the lockstep path.  Takes the int8 network-view boards
+  the select kernel wrote ([N, cell_stride]) and returns fp32 value [N] and
+  fp32 logits over all n*n tiles [N, n*n]; BatchNorm is folded into the
+  convolutions, activations are bf16 channels-last.  Gathering the legal
+  tiles and the masked softmax happen in the expand kernel
+  (AZ_PRIOR_LOGITS), not here.
+
+The network is the only dense contraction on the path and stays a PyTorch
+(cuDNN / cuBLAS) call by design; the tree kernels around it are ours.
+"""
+import logging
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+
+def conv3x3(cin, cout):
+    return nn.Conv2d(cin, cout, kernel_size=3, padding=1, bias=False)
+
+
+def conv1x1(cin, cout):
+    return nn.Conv2d(cin, cout, kernel_size=1, bias=False)
+
+
+class Resblock(nn.Module):
+    """network.py:17-39 (in_dim == dim on this path: no projection)."""
+
+    def __init__(self, in_dim, dim):
+        super().__init__()
+        self.conv1 = conv3x3(in_dim, dim)
+        self.bn1 = nn.BatchNorm2d(dim)
+        self.conv2 = conv3x3(dim, dim)
+        self.bn2 = nn.BatchNorm2d(dim)
+        if dim != in_dim:
+            self.res_conv = conv1x1(in_dim, dim)
+            self.res_bn = nn.BatchNorm2d(dim)
+        else:
+            self.res_conv = self.res_bn = None
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = self.bn2(self.conv2(y))
+        if self.res_conv is not None:
+            x = self.res_bn(self.res_conv(x))
+        return F.relu(y + x)
+
+
+def _fold(conv, bn):
+    """conv (no bias) followed by eval-mode BatchNorm -> weight, bias."""
+    scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+    return conv.weight * scale[:, None, None, None], \
+        bn.bias - bn.running_mean * scale
+
+
+class HexNetwork(nn.Module):
+    def __init__(self, board_size=11, num_blocks=6, base_chans=64):
+        super().__init__()
+        self.board_size = board_size
+        value_chans, policy_chans, input_dim = 2, 4, 4
+        nn2 = board_size * board_size
+        self.conv1 = conv3x3(input_dim, base_chans)
+        self.bn1 = nn.BatchNorm2d(base_chans)
+        self.resblocks = nn.Sequential(
+            *[Resblock(base_chans, base_chans) for _ in range(num_blocks)])
+        self.value_conv1 = conv1x1(base_chans, value_chans)
+        self.value_bn1 = nn.BatchNorm2d(value_chans)
+        self.value_fc2 = nn.Linear(value_chans * nn2, 64)
+        self.value_fc3 = nn.Linear(64, 1)
+        self.move_conv1 = conv1x1(base_chans, policy_chans)
+        self.move_bn1 = nn.BatchNorm2d(policy_chans)
+        self.encoder = nn.Embedding(3, 4)
+        self.move_fc = nn.Linear(policy_chans * nn2, nn2)
+        self._fast = None
+        nnet = sum(p.nelement() for p in self.parameters())
+        nenc = sum(p.nelement() for p in self.encoder.parameters())
+        logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)
+
+    @property
+    def device(self):
+        return self.conv1.weight.device
+
+    # ------------------------------------------------ reference interface --
+    def _trunk(self, x):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x = self.resblocks(x)
+        v = F.relu(self.value_bn1(self.value_conv1(x)))
+        v = F.relu(self.value_fc2(v.flatten(1)))
+        value = torch.tanh(self.value_fc3(v)).squeeze(1)
+        p = F.relu(self.move_bn1(self.move_conv1(x)))
+        return value, p.flatten(1)
+
+    def forward(self, x, legal_moves):
+        """network.py:134-152.  x int32 [B, n, n] (first-player view),
+        legal_moves int32 [B, K] zero padded."""
+        x = self.encoder(x.long()).permute(0, 3, 1, 2).contiguous()
+        value, p = self._trunk(x)
+        logit = self.move_fc(p)
+        tiles = (legal_moves - 1).clamp(min=0)
+        logit = torch.gather(logit, 1, tiles.long())
+        logit = logit.masked_fill(legal_moves == 0, -99)
+        return dict(value=value, moves_logprob=F.log_softmax(logit, dim=1))
+
+    def run(self, batch, *, compute_loss=False):
+        """network.py:87-105."""
+        output = self.forward(batch['board'], batch['legal_moves'])
+        if not compute_loss:
+            return {k: v.detach() for k, v in output.items()}
+        moves_prob = batch['moves_prob']
+        value_loss = F.mse_loss(output['value'], batch['reward'])
+        moves_loss = -(moves_prob * output['moves_logprob']).sum() \
+            / len(moves_prob)
+        loss = value_loss.to(moves_loss.device) + moves_loss
+        output = {k: v.detach() for k, v in output.items()}
+        output.update(value_loss=value_loss.item(),
+                      moves_loss=moves_loss.item())
+        return output, loss
+
+    # ------------------------------------------------------- lockstep path --
+    @torch.no_grad()
+    def prepare_inference(self, dtype=torch.bfloat16):
+        """Fold BatchNorm into the convolutions and cast for inference."""
+        assert not self.training, 'call .eval() first'
+        dev = self.device
+
+        def pack(w, b):
+            return (w.to(dev, dtype).contiguous(memory_format=torch.channels_last),
+                    b.to(dev, dtype).contiguous())
+
+        fast = {'dtype': dtype}
+        fast['emb'] = self.encoder.weight.to(dev, dtype).contiguous()
+        fast['stem'] = pack(*_fold(self.conv1, self.bn1))
+        fast['blocks'] = [(pack(*_fold(b.conv1, b.bn1)),
+                           pack(*_fold(b.conv2, b.bn2)))
+                          for b in self.resblocks]
+        # the two 1x1 head convolutions read the same activations: one conv
+        wv, bv = _fold(self.value_conv1, self.value_bn1)
+        wp, bp = _fold(self.move_conv1, self.move_bn1)
+        fast['heads'] = pack(torch.cat([wv, wp]), torch.cat([bv, bp]))
+        fast['nv'] = wv.shape[0]
+        fast['value_fc2'] = (self.value_fc2.weight.to(dev, dtype),
+                             self.value_fc2.bias.to(dev, dtype))
+        fast['value_fc3'] = (self.value_fc3.weight.to(dev, dtype),
+                             self.value_fc3.bias.to(dev, dtype))
+        fast['move_fc'] = (self.move_fc.weight.to(dev, dtype),
+                           self.move_fc.bias.to(dev, dtype))
+        self._fast = fast
+        return self
+
+    @torch.no_grad()
+    def evaluate_cells(self, cells):
+        """int8 [N, >= n*n] network-view boards -> value f32 [N], logits
+        f32 [N, n*n] over tiles (no legal-move gather, no softmax)."""
+        f = self._fast
+        if f is None:
+            raise RuntimeError('call prepare_inference() first')
+        n = self.board_size
+        N = cells.shape[0]
+        idx = cells[:, :n * n].to(torch.int32)
+        # [N, n, n, 4] in memory == channels-last [N, 4, n, n]
+        x = F.embedding(idx, f['emb']).view(N, n, n, 4).permute(0, 3, 1, 2)
+        x = F.relu_(F.conv2d(x, *f['stem'], padding=1))
+        for (w1, b1), (w2, b2) in f['blocks']:
+            y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+            y = F.conv2d(y, w2, b2, padding=1)
+            x = F.relu_(y.add_(x))
+        h = F.relu_(F.conv2d(x, *f['heads']))
+        nv = f['nv']
+        v = F.relu_(F.linear(h[:, :nv].flatten(1), *f['value_fc2']))
+        value = torch.tanh(F.linear(v, *f['value_fc3'])).squeeze(1)
+        logits = F.linear(h[:, nv:].flatten(1), *f['move_fc'])
+        return value.float(), logits.float()

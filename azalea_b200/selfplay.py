@@ -1,0 +1,195 @@
+"""Lockstep self-play: thousands of games advance one move at a time on one
+GPU, sharded by game index across GPUs.
+
+Replaces the reference's process-per-game data parallelism
+(azalea/parallel_player.py:17-76, azalea/process_pool.py:15-47,
+azalea/play_game.py:18-78) for the self-play path.  One ``step_move()`` is
+what ``AzaleaAgent.choose_action`` + ``execute_action`` do for one game
+(azalea_agent.py:54-64), done for every resident game:
+
+    select_root -> evaluate -> expand_root          (mcts.evaluate_root)
+    num_batches x [ select -> evaluate -> expand_backup ]   (mcts.sample_paths)
+    play_commit                                      (policy.py:160-176, play_game.py:46-67)
+
+Everything between two host calls stays on the device; with
+``cuda_graph=True`` the whole move is one CUDA graph launch.  Games are
+independent: rank r of W owns global games [r*G, (r+1)*G), each game's
+Philox stream is keyed by its global id, so results do not depend on the
+world size.  The only exchange is the replay gather to rank 0.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .engine import Engine, decode_replay_rows
+from .replay_buffer import ReplayDataFrame
+from .search_tree import as_distribution
+from .typing import GameState
+
+
+class StubEvaluator:
+    """Deterministic device stub (test / bench aid; modes as in
+    oracle/azalea_oracle.h): 0 uniform, 1 dyadic, 2 rough."""
+
+    def __init__(self, mode=0):
+        self.mode = int(mode)
+
+
+class LockstepSelfPlay:
+    def __init__(self, evaluator, *, num_games=4096, board_size=11,
+                 simulations=800, search_batch_size=10, exploration_coef=0.5,
+                 exploration_depth=15, exploration_noise_alpha=0.03,
+                 exploration_noise_scale=0.25, exploration_temperature=1.0,
+                 move_sampling=True, move_exploration=True, seed=0,
+                 device=None, rank=0, world_size=1, nodes_per_game=None,
+                 replay_rows=None, collect_replay=True, cuda_graph=True,
+                 max_plies=300):
+        self.evaluator = evaluator
+        self.G = int(num_games)
+        self.n = int(board_size)
+        self.nn = self.n * self.n
+        self.batch = int(search_batch_size)
+        # mcts.py:268: num_batches = sims // batch + 1
+        self.num_batches = int(simulations) // self.batch + 1
+        self.sims_per_move = self.num_batches * self.batch
+        self.coef = float(exploration_coef)
+        self.depth = int(exploration_depth)
+        self.temperature = float(exploration_temperature)
+        self.move_sampling = bool(move_sampling)
+        # policy.py:142-147: noise only when sampling and exploring
+        self.noise_scale = float(exploration_noise_scale) \
+            if (move_sampling and move_exploration) else 0.0
+        self.noise_alpha = float(exploration_noise_alpha)
+        self.collect_replay = bool(collect_replay)
+        if replay_rows is None:
+            replay_rows = 2 * self.G * min(self.nn, max_plies) if collect_replay else 0
+        if nodes_per_game is None:
+            nodes_per_game = 2 * (self.sims_per_move + 1) * self.nn
+        self.eng = Engine(self.G, self.n, max_batch=self.batch,
+                          nodes_per_game=nodes_per_game,
+                          replay_rows=replay_rows, max_plies=max_plies,
+                          seed=seed, first_game_id=rank * self.G,
+                          game_id_stride=world_size * self.G, device=device)
+        self.device = self.eng.device
+        self.chosen = torch.zeros(self.G, 4, dtype=torch.int32,
+                                  device=self.device)
+        self.is_stub = isinstance(evaluator, StubEvaluator)
+        if not self.is_stub:
+            if getattr(evaluator, '_fast', None) is None:
+                evaluator.eval()
+                evaluator.to(self.device)
+                evaluator.prepare_inference()
+            torch.backends.cudnn.benchmark = True
+        self.moves_done = 0
+        self._graph = None
+        self._want_graph = bool(cuda_graph)
+        # kernels of ours launched per move (for bench.py's gpu_launches)
+        self.launches_per_move = 3 + self.num_batches * (3 if self.is_stub else 2) \
+            + (1 if self.is_stub else 0)
+
+    # ------------------------------------------------------------ one move --
+    def _evaluate(self, root):
+        """Leaves -> (value, prior/logits, kind)."""
+        eng = self.eng
+        if self.is_stub:
+            eng.stub_eval(self.evaluator.mode)
+            return None, None, _cabi.AZ_PRIOR_PROBS
+        if root:
+            value, logits = self.evaluator.evaluate_cells(eng.leaf_board[:, 0])
+            eng.prior[:, 0].copy_(logits)
+            return None, None, _cabi.AZ_PRIOR_LOGITS
+        cells = eng.leaf_board.view(self.G * self.batch, eng.cell_stride)
+        value, logits = self.evaluator.evaluate_cells(cells)
+        return value.contiguous(), logits.contiguous(), _cabi.AZ_PRIOR_LOGITS
+
+    def _move_body(self):
+        eng = self.eng
+        eng.select_root()
+        _, _, kind = self._evaluate(True)
+        eng.expand_root(None, kind)
+        for _ in range(self.num_batches):
+            eng.select(self.batch, self.coef, self.noise_scale,
+                       self.noise_alpha)
+            value, prior, kind = self._evaluate(False)
+            eng.expand_backup(value, prior, kind)
+            # keep evaluator outputs alive until the kernel that reads them
+            # has been enqueued (same stream: safe to drop afterwards)
+        eng.play_commit(self.temperature, self.depth, self.move_sampling,
+                        self.collect_replay, True, self.chosen)
+
+    def capture(self, warmup=2):
+        """Warm up eagerly (cuDNN autotune), then capture one move as a
+        CUDA graph."""
+        for _ in range(warmup):
+            self._move_body()
+            self.moves_done += 1
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._move_body()
+        self.moves_done += 1
+        self._graph = graph
+
+    def step_move(self):
+        """One move of every game (enqueue only; no host sync)."""
+        if self._want_graph and self._graph is None:
+            self.capture()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._move_body()
+        self.moves_done += 1
+
+    # -------------------------------------------------------------- output --
+    def harvest(self):
+        """Finished games' replay rows (host, raw uint8 [R, row_bytes])."""
+        return self.eng.harvest_replay()
+
+    def counters(self):
+        return self.eng.counter_totals()
+
+
+def rows_to_dataframe(rows, board_size) -> ReplayDataFrame:
+    """Raw replay rows -> the reference's ``ReplayDataFrame``
+    (replay_buffer.py:25-104, play_game.py:63-67,90-96): state before the
+    move, pi = as_distribution(visits, temperature) as float32, reward."""
+    h, boards, visits = decode_replay_rows(rows, board_size)
+    df = ReplayDataFrame()
+    for i in range(len(h)):
+        board = boards[i].astype(np.int32)
+        legal = np.flatnonzero(board.ravel() == 0).astype(np.int32) + 1
+        k = int(h['num_moves'][i])
+        assert k == len(legal)
+        df.state.append(GameState(int(h['color'][i]), legal, 0, board))
+        df.moves_prob.append(
+            as_distribution(visits[i, :k], float(h['temperature'][i]))
+            .astype(np.float32))
+        df.reward.append(np.float32(h['reward'][i]))
+    return df
+
+
+def gather_replay_rows(rows: torch.Tensor, dst: int = 0, group=None):
+    """The path's only exchange: variable-length row blocks to rank ``dst``
+    (NCCL on device tensors, gloo on host tensors).  Returns the
+    concatenated rows on ``dst`` and None elsewhere."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return rows
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    count = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.zeros(cap, rows.shape[1], dtype=rows.dtype,
+                         device=rows.device)
+    padded[:rows.shape[0]] = rows
+    bufs = [torch.zeros_like(padded) for _ in range(world)] \
+        if rank == dst else None
+    dist.gather(padded, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)])

@@ -84,12 +84,14 @@ enum {
     AZ_BUF_PRIOR = 3,       /* f32   [G][max_batch][n*n]      evaluator output (priors or logits) */
     AZ_BUF_META = 4,        /* int32 [G][16] */
     AZ_BUF_REPLAY = 5,      /* uint8 [replay_rows][replay_row_bytes] */
-    AZ_BUF_COUNTERS = 6,    /* int64 [16] engine-wide counters */
+    AZ_BUF_COUNTERS = 6,    /* int64 [G][16] per-game counters (sum over games on the host) */
     AZ_BUF_LEAF_MOVES = 7,  /* int32 [G][max_batch][n*n] network-view legal moves, 0-padded */
-    AZ_BUF__COUNT = 8
+    AZ_BUF_GLOBALS = 8,     /* int64 [16]: [0] = replay append cursor (rows) */
+    AZ_BUF__COUNT = 9
 };
 
-/* engine-wide counters (AZ_BUF_COUNTERS) */
+/* counter columns (AZ_BUF_COUNTERS); each game's warp owns its row, so the
+ * hot kernels never contend on an atomic */
 enum {
     AZ_CNT_SIMULATIONS = 0,   /* root-to-leaf descents */
     AZ_CNT_SUM_CHILDREN = 1,  /* sum over descents and levels of k */
@@ -145,11 +147,13 @@ int az_hex_state(az_engine *e, int8_t *board_dev, int32_t *color_dev,
 int az_hex_legal_moves(az_engine *e, int32_t *moves_dev, int32_t *count_dev,
                        void *stream);
 /* Overwrite root positions (HexGame.__setstate__, hex.py:39-45): board
- * int8[G][n*n], colour to move 1/2.  Trees are reset.  Winner is recomputed
- * from `last_tile_dev` (nullable; -1 = none). */
+ * int8[G][n*n], colour to move 1/2.  The winner is recomputed from
+ * `last_tile_dev` (nullable; -1 = none).  reset_trees != 0 also clears the
+ * search trees (Policy.reset); 0 keeps them (the caller vouches that the
+ * tree root is this position, as SearchTree.search does). */
 int az_hex_set_state(az_engine *e, const int8_t *board_dev,
                      const int32_t *color_dev, const int32_t *last_tile_dev,
-                     void *stream);
+                     int reset_trees, void *stream);
 
 /* ----------------------------------------------------------------- search */
 

@@ -330,8 +330,51 @@ def gen_formulas():
     print('formulas.npz', len(out), 'arrays')
 
 
+def gen_network():
+    """The reference's HexNetwork (with the torch>=2 contiguity shim, SURVEY
+    8c) loaded with azalea_b200's seed-0 state_dict, on fixed inputs."""
+    import torch
+    import torch.nn.functional as F
+    from azalea.network import HexNetwork as RefNet, Network as RefBase
+    from azalea_b200.network import HexNetwork
+    torch.manual_seed(0)
+    mine = HexNetwork(11, 6, 64).eval()
+    gen = torch.Generator().manual_seed(1)
+    for m in mine.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=gen) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=gen) * 0.1)
+    ref = RefNet(11, 6, 64)
+    ref.load_state_dict(mine.state_dict())
+    ref.eval()
+    rng = np.random.RandomState(5)
+    B = 9
+    board = rng.randint(0, 3, size=(B, 11, 11)).astype(np.int32)
+    lm = np.zeros((B, 121), np.int32)
+    for i in range(B):
+        e = np.flatnonzero(board[i].ravel() == 0) + 1
+        lm[i, :len(e)] = e
+    lm = lm[:, :(lm > 0).sum(1).max()]
+    with torch.no_grad():
+        x = ref.encoder(torch.tensor(board).long()).permute(0, 3, 1, 2).contiguous()
+        value, p = RefBase.forward(ref, x)
+        logit = ref.move_fc(p)
+        tl = torch.tensor(lm)
+        logit = torch.gather(logit, 1, (tl - 1).clamp(min=0).long())
+        logit.masked_fill_(tl == 0, -99)
+        logp = F.log_softmax(logit, dim=1)
+    np.savez_compressed(os.path.join(HERE, 'network.npz'), board=board,
+                        legal_moves=lm, value=value.numpy(),
+                        moves_logprob=logp.numpy())
+    print('network.npz')
+
+
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['hex', 'formulas', 'mcts']
+    which = sys.argv[1:] or ['hex', 'formulas', 'mcts', 'network']
+    if 'network' in which:
+        gen_network()
     if 'hex' in which:
         gen_hex_rules()
     if 'formulas' in which:

@@ -1,0 +1,140 @@
+"""Host-side logic that needs no GPU: distribution maths, perspective flip,
+network parity with the reference's architecture, replay row decoding,
+multi-rank replay gather (gloo, world size 2)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from azalea_b200 import as_distribution
+from azalea_b200.game.hex import HexGame
+from azalea_b200.network import HexNetwork
+
+
+def test_as_distribution_golden(golden_formulas):
+    f = golden_formulas
+    for i in range(len(f['dist_k'])):
+        k = int(f['dist_k'][i])
+        got = as_distribution(f['dist_counts'][i][:k].copy(),
+                              float(f['dist_temp'][i]))
+        assert got.dtype == np.float64
+        assert got.tobytes() == f['dist_out'][i][:k].tobytes()
+
+
+@pytest.mark.parametrize('n', (3, 5, 11, 19))
+def test_flip_golden(golden_hex, n):
+    g = golden_hex
+    fb, fm = HexGame.flip_player_board_moves(g[f'n{n}_flip_in_board'],
+                                             g[f'n{n}_flip_in_moves'])
+    assert (fb == g[f'n{n}_flip_out_board']).all()
+    assert (fm == g[f'n{n}_flip_out_moves']).all()
+    one_b, one_m = HexGame.flip_player_board_moves(
+        g[f'n{n}_flip_in_board'][0], g[f'n{n}_flip_in_moves'][0])
+    assert (one_b[0] == fb[0]).all() and (one_m[0] == fm[0]).all()
+
+
+def test_network_matches_reference_architecture():
+    """Golden: the reference's HexNetwork, given this module's seed-0
+    state_dict, on fixed inputs (tests/golden/make_golden.py:gen_network)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'network.npz'))
+    torch.manual_seed(0)
+    net = HexNetwork(11, 6, 64).eval()
+    # give BatchNorm non-trivial statistics, deterministically
+    gen = torch.Generator().manual_seed(1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=gen) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=gen) * 0.1)
+    board = torch.from_numpy(g['board'])
+    moves = torch.from_numpy(g['legal_moves'])
+    with torch.no_grad():
+        out = net.run(dict(board=board, legal_moves=moves))
+        assert np.allclose(out['value'].numpy(), g['value'], atol=1e-6)
+        assert np.allclose(out['moves_logprob'].numpy(), g['moves_logprob'], atol=1e-5)
+        # folded fp32 fast path == reference path
+        net.prepare_inference(torch.float32)
+        cells = torch.zeros(len(board), 128, dtype=torch.int8)
+        cells[:, :121] = board.view(len(board), -1).to(torch.int8)
+        value, logits = net.evaluate_cells(cells)
+        lg = torch.gather(logits, 1, (moves - 1).clamp(min=0).long())
+        lg = lg.masked_fill(moves == 0, -99)
+        assert np.allclose(value.numpy(), g['value'], atol=1e-5)
+        assert np.allclose(torch.log_softmax(lg, 1).numpy(), g['moves_logprob'], atol=1e-4)
+
+
+def test_decode_replay_rows_layout():
+    from azalea_b200.engine import (ROW_HEADER, decode_replay_rows,
+                                    replay_row_bytes)
+    n, nn, cs = 5, 25, 32
+    hb = ROW_HEADER.itemsize
+    assert hb == 48
+    row_bytes = replay_row_bytes(n)
+    rows = np.zeros((2, row_bytes), dtype=np.uint8)
+    h = np.zeros(2, dtype=ROW_HEADER)
+    h['game_id'] = [7, 1 << 40]
+    h['ply'] = [3, 4]
+    h['reward'] = [1.0, -1.0]
+    rows[:, :hb] = h.view(np.uint8).reshape(2, hb)
+    rows[0, hb:hb + nn] = np.arange(nn) % 3
+    vis = np.arange(nn, dtype='<f4')
+    rows[1, hb + cs:hb + cs + 4 * nn] = vis.view(np.uint8)
+    hh, board, visits = decode_replay_rows(rows, n)
+    assert list(hh['game_id']) == [7, 1 << 40] and list(hh['ply']) == [3, 4]
+    assert (board[0].ravel() == np.arange(nn) % 3).all()
+    assert (visits[1] == vis).all()
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from azalea_b200.selfplay import gather_replay_rows
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}',
+                            rank=rank, world_size=world)
+    # rank r contributes r + 2 rows whose bytes identify (rank, row)
+    rows = torch.zeros(rank + 2, 48, dtype=torch.uint8)
+    for i in range(rank + 2):
+        rows[i] = 16 * rank + i
+    out = gather_replay_rows(rows, dst=0)
+    q.put((rank, None if out is None else out.numpy().copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_replay_gather_two_ranks_gloo():
+    """Replay rows of game shards reach rank 0 in rank order."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q))
+             for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[1] is None
+    assert got[0].shape == (5, 48)
+    assert list(got[0][:, 0]) == [0, 1, 16, 17, 18]
+
+
+def test_game_sharding_is_world_size_invariant():
+    """Global game ids: rank r of W owns [r*G, (r+1)*G); a slot's successive
+    games advance by W*G, so the id sets of different ranks never meet."""
+    G, W = 4, 3
+    seen = set()
+    for rank in range(W):
+        for slot in range(G):
+            for serial in range(5):
+                gid = rank * G + slot + serial * W * G
+                assert gid not in seen
+                seen.add(gid)
+    assert seen == set(range(5 * W * G))

@@ -1,0 +1,290 @@
+"""GPU parity: the search kernels vs golden traces of the Python reference
+and vs the C oracle.  Visit counts, total values, priors, node counts and
+root statistics are compared bit for bit; chosen moves follow."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import stubs
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).tobytes()
+
+
+class GpuTree:
+    """One-game engine driven with the device stub evaluator."""
+
+    def __init__(self, n, batch, mode, **kw):
+        from azalea_b200 import Engine
+        self.eng = Engine(1, n, max_batch=batch, **kw)
+        self.batch, self.mode = batch, mode
+
+    def search(self, sims, coef):
+        e = self.eng
+        if int(e.root_stats()[3].item()) < 0:
+            e.select_root()
+            e.stub_eval(self.mode)
+            e.expand_root()
+        for _ in range(sims // self.batch + 1):
+            e.select(self.batch, coef)
+            e.stub_eval(self.mode)
+            e.expand_backup()
+
+    def stats(self):
+        v, w, p, k, rnw, nodes = self.eng.root_stats()
+        k = int(k.item())
+        return (v[0, :k].cpu().numpy(), w[0, :k].cpu().numpy(),
+                p[0, :k].cpu().numpy(), rnw[0].cpu().numpy(),
+                int(nodes.item()))
+
+
+def trace_names(g, iface):
+    names = sorted({k.split('/')[0] for k in g.files})
+    return [nm for nm in names if not nm.startswith('match')
+            and str(g[f'{nm}/iface']) == iface]
+
+
+def test_golden_traces_device_stub(golden_mcts):
+    """Exact-prior traces (whole games on 3x3 .. 19x19, batch sizes 1..16,
+    four c_puct values): after every search the root matches the reference
+    bit for bit; the recorded moves are then played."""
+    g = golden_mcts
+    names = trace_names(g, 'patch')
+    assert len(names) >= 10
+    for name in names:
+        n, sims, batch, mode = (int(x) for x in g[f'{name}/config'][:4])
+        coef = float(g[f'{name}/coef'])
+        t = GpuTree(n, batch, mode)
+        for ply in range(len(g[f'{name}/move'])):
+            t.search(sims, coef)
+            k = int(g[f'{name}/k'][ply])
+            v, w, p, rnw, nodes = t.stats()
+            where = (name, ply)
+            assert len(v) == k, where
+            assert bits(v) == bits(g[f'{name}/visits'][ply][:k]), where
+            assert bits(w) == bits(g[f'{name}/total_value'][ply][:k]), where
+            assert bits(p) == bits(g[f'{name}/prior'][ply][:k]), where
+            assert bits(rnw[0]) == bits(g[f'{name}/root_visits'][ply]), where
+            assert bits(rnw[1]) == bits(g[f'{name}/root_value'][ply]), where
+            assert nodes == g[f'{name}/num_nodes'][ply], where
+            move_id = int(g[f'{name}/move_id'][ply])
+            t.eng.tree_move([move_id])
+            res = int(t.eng.hex_step([int(g[f'{name}/move'][ply])]).item())
+            assert int(t.eng.status().item()) == 0, where
+        assert res == int(g[f'{name}/result'])
+
+
+def make_agent(n, sims, batch, coef, mode, depth=15):
+    import azalea_b200 as az
+    p = az.Policy()
+    p.net = stubs.StubNet(mode)
+    p.simulations, p.search_batch_size, p.exploration_coef = sims, batch, coef
+    p.exploration_depth = depth
+    p.exploration_noise_alpha, p.exploration_noise_scale = 0.03, 0.25
+    p.exploration_temperature = 1.0
+    return az.AzaleaAgent(lambda: az.HexGame(n), policy=p)
+
+
+def test_dropin_agent_reproduces_reference_games(golden_mcts):
+    """The reference's own calling sequence -- AzaleaAgent.seed /
+    choose_action / execute_action with an evaluator object plugged into
+    Policy.net -- reproduces the reference's moves, probabilities, value,
+    metrics and tree statistics."""
+    g = golden_mcts
+    for name in trace_names(g, 'run'):
+        n, sims, batch, mode, seed, sampling, depth = \
+            (int(x) for x in g[f'{name}/config'])
+        agent = make_agent(n, sims, batch, float(g[f'{name}/coef']), mode, depth)
+        agent.reset()
+        agent.seed(seed)
+        agent.settings['move_sampling'] = bool(sampling)
+        for ply in range(len(g[f'{name}/move'])):
+            move = agent.choose_action()
+            where = (name, ply)
+            k = int(g[f'{name}/k'][ply])
+            v, w, p, rn, rw = agent.policy.tree.root_stats()
+            assert bits(v) == bits(g[f'{name}/visits'][ply][:k]), where
+            assert bits(w) == bits(g[f'{name}/total_value'][ply][:k]), where
+            assert bits(p) == bits(g[f'{name}/prior'][ply][:k]), where
+            assert move == g[f'{name}/move'][ply], where
+            info = agent.info
+            assert info['move_id'] == g[f'{name}/move_id'][ply]
+            assert info['moves_prob'].tobytes() == g[f'{name}/probs'][ply][:k].tobytes()
+            assert bits(info['value']) == bits(g[f'{name}/value'][ply])
+            m = info['metrics']
+            assert m['search_tree_nodes'] == g[f'{name}/num_nodes'][ply], where
+            assert np.isclose(m['search_value'], g[f'{name}/search_value'][ply], atol=1e-6)
+            assert m['search_root_children'] == k
+            result = agent.execute_action(move)
+        if len(g[f'{name}/move']) > 20:
+            assert result == int(g[f'{name}/result'])
+
+
+def test_survey_known_answers_dropin():
+    """uniform stub, 11x11, 800 sims, batch 10, c 0.5, seed 7."""
+    agent = make_agent(11, 800, 10, 0.5, stubs.UNIFORM)
+    agent.reset()
+    agent.seed(7)
+    moves, nodes = [], []
+    for ply in range(3):
+        moves.append(int(agent.choose_action()))
+        nodes.append(int(agent.info['metrics']['search_tree_nodes']))
+        if ply == 0:
+            v = agent.policy.tree.root_stats()[0]
+            assert (v[:84] == 7).all() and (v[84:] == 6).all()
+        agent.execute_action(moves[-1])
+    assert moves == [30, 17, 57]
+    assert nodes == [96633, 192327, 287210]
+
+
+@pytest.mark.parametrize('name', ('match7', 'match5'))
+def test_two_tree_match(golden_mcts, name):
+    """Two trees per game: opponent moves re-root or reset the other tree
+    (search_tree.py:115-132, play_game.py:47-48)."""
+    g = golden_mcts
+    cfg = g[f'{name}/config']
+    n, mode = int(cfg[0]), int(cfg[5])
+    sims, batch = (int(cfg[1]), int(cfg[3])), (int(cfg[2]), int(cfg[4]))
+    coef = [float(x) for x in g[f'{name}/coef']]
+    trees = [GpuTree(n, batch[0], mode), GpuTree(n, batch[1], mode)]
+    for ply in range(len(g[f'{name}/move'])):
+        a = ply % 2
+        trees[a].search(sims[a], coef[a])
+        k = int(g[f'{name}/k'][ply])
+        v, w, p, rnw, nodes = trees[a].stats()
+        assert bits(v) == bits(g[f'{name}/visits'][ply][:k]), ply
+        assert bits(w) == bits(g[f'{name}/total_value'][ply][:k]), ply
+        assert nodes == g[f'{name}/num_nodes'][ply], ply
+        for t in trees:
+            t.eng.tree_move([int(g[f'{name}/move_id'][ply])])
+            res = int(t.eng.hex_step([int(g[f'{name}/move'][ply])]).item())
+    assert res == int(g[f'{name}/result'])
+
+
+@pytest.mark.parametrize('n,G,sims,batch,coef,mode,plies', (
+    (11, 256, 800, 10, 0.5, stubs.ROUGH, 12),
+    (11, 64, 320, 32, 1.25, stubs.DYADIC, 40),
+    (7, 512, 200, 8, 0.5, stubs.ROUGH, 49),
+    (19, 16, 400, 10, 0.5, stubs.ROUGH, 6),
+    (5, 256, 60, 5, 2.0, stubs.ROUGH, 25),
+))
+def test_lockstep_games_vs_oracle(n, G, sims, batch, coef, mode, plies):
+    """Many different games searched in lockstep on the GPU against the C
+    oracle, one oracle tree per game.  Each game follows its own line (the
+    g-th most visited move, ties to the lowest index), so the trees differ."""
+    from azalea_b200 import Engine
+    eng = Engine(G, n, max_batch=batch)
+    games = [oracle.Hex(n) for _ in range(G)]
+    trees = [oracle.Tree(max_nodes=3_000_000) for _ in range(G)]
+    alive = np.ones(G, dtype=bool)
+    for ply in range(plies):
+        eng.select_root()
+        eng.stub_eval(mode)
+        eng.expand_root()
+        for _ in range(sims // batch + 1):
+            eng.select(batch, coef)
+            eng.stub_eval(mode)
+            eng.expand_backup()
+        v, w, p, k, rnw, nodes = (x.cpu().numpy() for x in eng.root_stats())
+        assert (eng.status().cpu().numpy()[alive] == 0).all()
+        move_ids = -np.ones(G, dtype=np.int32)
+        moves = np.zeros(G, dtype=np.int32)
+        for gi in np.flatnonzero(alive):
+            trees[gi].sample_paths_stub(games[gi], sims, batch, coef, mode)
+            ov, ow, op = trees[gi].root_stats()
+            kk = len(ov)
+            where = (ply, gi)
+            assert k[gi] == kk, where
+            assert bits(v[gi, :kk]) == bits(ov), where
+            assert bits(w[gi, :kk]) == bits(ow), where
+            assert bits(p[gi, :kk]) == bits(op), where
+            rn, rw = trees[gi].root_node()
+            assert bits(rnw[gi]) == bits([rn, rw]), where
+            assert nodes[gi] == trees[gi].num_nodes, where
+            order = np.argsort(-ov, kind='stable')
+            mid = int(order[(gi + ply) % min(kk, 3)])
+            move_ids[gi] = mid
+            moves[gi] = games[gi].legal_moves()[mid]
+            trees[gi].move(mid)
+            games[gi].step(int(moves[gi]))
+        eng.tree_move(move_ids)
+        res = eng.hex_step(moves).cpu().numpy()
+        for gi in np.flatnonzero(alive):
+            assert res[gi] == games[gi].result()
+            if res[gi]:
+                alive[gi] = False
+        if not alive.any():
+            break
+    cnt = eng.counter_totals()
+    assert cnt['simulations'] > 0 and cnt['sum_depth'] >= cnt['simulations']
+
+
+def test_search_tree_full_is_raised():
+    """search_tree.MAX_NODES emulation: SearchTreeFull (search_tree.py:258)."""
+    import azalea_b200 as az
+    from azalea_b200 import search_tree
+    old = search_tree.MAX_NODES
+    search_tree.MAX_NODES = 5000
+    try:
+        agent = make_agent(11, 800, 10, 0.5, stubs.UNIFORM)
+        agent.reset()
+        agent.seed(1)
+        with pytest.raises(az.SearchTreeFull):
+            agent.choose_action()
+    finally:
+        search_tree.MAX_NODES = old
+    # the oracle raises at the same limit
+    t = oracle.Tree(max_nodes=5000)
+    with pytest.raises(oracle.SearchTreeFull):
+        t.sample_paths_stub(oracle.Hex(11), 800, 10, 0.5, 0)
+
+
+def test_pool_overflow_is_flagged_not_corrupting():
+    from azalea_b200 import Engine, _cabi
+    eng = Engine(4, 11, max_batch=10, nodes_per_game=2000)
+    eng.select_root(); eng.stub_eval(0); eng.expand_root()
+    for _ in range(40):
+        eng.select(10, 0.5); eng.stub_eval(0); eng.expand_backup()
+    st = eng.status().cpu().numpy()
+    assert (st == _cabi.AZ_ST_POOL_FULL).all()
+    v, _, _, k, _, _ = eng.root_stats()
+    assert (k.cpu().numpy() == 121).all()
+    assert float(v.sum()) > 0
+
+
+def test_reroot_compaction_preserves_subtree():
+    """Re-rooting copies the kept subtree; searching on from it gives the
+    same statistics as the reference, which keeps everything in place
+    (covered ply by ply by the golden traces); here: the kept child's own
+    N/W survive the move."""
+    t = GpuTree(7, 10, stubs.ROUGH)
+    t.search(300, 0.5)
+    v, w, p, rnw, _ = t.stats()
+    mid = int(np.argmax(v))
+    t.eng.tree_move([mid])
+    v2, w2, p2, rnw2, _ = t.stats()
+    assert bits(rnw2[0]) == bits(v[mid]) and bits(rnw2[1]) == bits(w[mid])
+    assert v2.sum() <= v[mid]
+
+
+def test_dirichlet_noise_statistics():
+    """Root noise (mcts.py:126-131) is only statistically comparable: with
+    epsilon = 1 the prior is pure Dirichlet(alpha) noise redrawn per
+    simulation, so visits spread over many more children than without."""
+    from azalea_b200 import Engine
+    G = 64
+    eng = Engine(G, 11, max_batch=10, seed=5)
+    eng.select_root(); eng.stub_eval(0); eng.expand_root()
+    for _ in range(30):
+        eng.select(10, 2.0, noise_scale=0.25, noise_alpha=0.03)
+        eng.stub_eval(0); eng.expand_backup()
+    v = eng.root_stats()[0].cpu().numpy()
+    # duplicate leaves inside a batch are backed up once (mcts.py:75)
+    assert (v.sum(1) <= 300).all() and (v.sum(1) >= 280).all()
+    assert (eng.status().cpu().numpy() == 0).all()
+    # different games draw different noise
+    assert len({v[g].tobytes() for g in range(G)}) > G // 2

@@ -204,6 +204,20 @@ __device__ __forceinline__ uint4 az_philox(uint4 c, uint2 k)
     return c;
 }
 
+// 7 rounds: the fewest that still pass BigCrush (Salmon et al., SC'11);
+// used for the per-simulation root noise, where the generator is the cost
+__device__ __forceinline__ uint4 az_philox7(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
 __device__ __forceinline__ float az_u01(uint32_t r)     // (0,1)
 {
     return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);

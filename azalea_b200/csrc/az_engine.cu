@@ -688,6 +688,11 @@ int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->meta, 0, (size_t)e->G * AZ_META_INTS * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->value, 0, (size_t)e->G * e->B * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->prior, 0, (size_t)e->G * e->B * e->nn * 4, 0));
+    // replay rows carry alignment padding that no kernel writes
+    if (rc == AZ_OK && e->hist_rows)
+        rc = az_check(cudaMemsetAsync(e->hist, 0, (size_t)e->G * e->hist_rows * e->row_bytes, 0));
+    if (rc == AZ_OK && e->cfg.replay_rows)
+        rc = az_check(cudaMemsetAsync(e->replay, 0, (size_t)e->cfg.replay_rows * e->row_bytes, 0));
     if (rc == AZ_OK) {
         k_reset<<<az_grid(e), AZ_WARPS_PER_CTA * 32, 0, 0>>>(*e, NULL, 1);
         rc = az_check(cudaGetLastError());
@@ -743,10 +748,13 @@ int az_hex_set_state(az_engine *e, const int8_t *board_dev, const int32_t *color
 
 static int az_select_launch(az_engine *e, const az_select_args &a, void *stream)
 {
+    const bool noise = a.noise_scale != 0.0 && !a.root_mode;
     if (e->NW <= 4) {
-        AZ_LAUNCH(k_select<4>, e, stream, a);
+        if (noise) AZ_LAUNCH((k_select<4, true>), e, stream, a);
+        AZ_LAUNCH((k_select<4, false>), e, stream, a);
     } else {
-        AZ_LAUNCH(k_select<12>, e, stream, a);
+        if (noise) AZ_LAUNCH((k_select<12, true>), e, stream, a);
+        AZ_LAUNCH((k_select<12, false>), e, stream, a);
     }
 }
 
@@ -827,6 +835,12 @@ int az_stub_eval(az_engine *e, int mode, void *stream)
 {
     if (!e || mode < 0 || mode > 2) return AZ_E_INVALID;
     AZ_LAUNCH(k_stub_eval, e, stream, mode);
+}
+
+int az_noise_sample(az_engine *e, float alpha, int k, int sim, float *out_dev, void *stream)
+{
+    if (!e || !out_dev || k < 1 || k > e->nn || alpha <= 0.0f) return AZ_E_INVALID;
+    AZ_LAUNCH(k_noise_sample, e, stream, alpha, k, sim, out_dev);
 }
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)

@@ -71,10 +71,90 @@ __device__ __forceinline__ void az_emit_board(const az_engine &e, uint32_t *smas
     }
 }
 
+// ------------------------------------------------------------- root noise
+
+// eta ~ Dirichlet(alpha) over k children, lane j%32 slot j/32 (mcts.py:126-127:
+// rng.dirichlet(np.full(k, alpha)); statistical parity, not bit parity).
+// eta = g / sum(g) with g ~ Gamma(alpha) by Ahrens-Dieter GS (exact for
+// alpha <= 1; larger alpha adds floor(alpha) exponentials), kept in logs
+// because alpha = 0.03 puts most samples far below FLT_MIN before
+// normalisation.  Counter-based: (simulation, child, ply) -> Philox4x32-7.
+template <int MAXS>
+__device__ __forceinline__ void az_dirichlet_noise(int k, float alpha, uint32_t sim,
+                                                   uint32_t ply, uint2 key, float (&noise)[MAXS])
+{
+    const int lane = az_lane();
+    const float alpha_frac = alpha > 1.0f ? alpha - floorf(alpha) : alpha;
+    const float agx = alpha_frac > 0.0f ? alpha_frac : 1.0f;
+    const float inv_alpha = 1.0f / agx;
+    const float bgs = (2.7182818f + agx) / 2.7182818f;
+    float lg[MAXS], mx = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < MAXS; s++) {
+        const int j = lane + 32 * s;
+        float r = -INFINITY;
+        if (j < k) {
+            for (uint32_t att = 0; att < 8u; att++) {
+                const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j, ply, 0xD1C10000u + att), key);
+                bool ok = false;
+#pragma unroll
+                for (int h = 0; h < 2 && !ok; h++) {
+                    const float pgs = bgs * az_u01(h ? u.z : u.x);
+                    const float lu2 = __logf(az_u01(h ? u.w : u.y));
+                    if (pgs <= 1.0f) {
+                        r = __logf(pgs) * inv_alpha;        // ln X, X = P^(1/alpha)
+                        ok = lu2 <= -__expf(r);             // U2 <= exp(-X)
+                    } else {
+                        const float xg = -__logf((bgs - pgs) * inv_alpha);
+                        r = __logf(xg);
+                        ok = lu2 <= (agx - 1.0f) * r;       // U2 <= X^(alpha-1)
+                    }
+                }
+                if (ok) break;
+            }
+            if (alpha > 1.0f) {
+                float tot = (alpha_frac > 0.0f) ? __expf(r) : 0.0f;
+                for (int m = 0; m < (int)alpha; m++) {
+                    const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j, ply, 0xE9000000u + m), key);
+                    tot -= __logf(az_u01(u.x));
+                }
+                r = __logf(tot);
+            }
+            mx = fmaxf(mx, r);
+        }
+        lg[s] = r;
+    }
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AZ_FULL, mx, off));
+    float z = 0.0f;
+#pragma unroll
+    for (int s = 0; s < MAXS; s++) { lg[s] = __expf(lg[s] - mx); z += lg[s]; }
+    for (int off = 16; off; off >>= 1) z += __shfl_xor_sync(AZ_FULL, z, off);
+    const float invz = 1.0f / z;
+#pragma unroll
+    for (int s = 0; s < MAXS; s++) noise[s] = lg[s] * invz;
+}
+
+// Test aid: draw the root noise vector each game would use for simulation
+// `sim` of its current ply into out[g][0..k).
+__global__ void k_noise_sample(az_engine e, float alpha, int k, int sim, float *out)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    const uint2 key = make_uint2((uint32_t)e.cfg.seed ^ (uint32_t)meta[M_GID_LO],
+                                 (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
+    float noise[12];
+    az_dirichlet_noise<12>(k, alpha, (uint32_t)sim, (uint32_t)meta[M_PLY], key, noise);
+#pragma unroll
+    for (int s = 0; s < 12; s++)
+        if (lane + 32 * s < k) out[(size_t)g * k + lane + 32 * s] = noise[s];
+}
+
 // ------------------------------------------------------------------ select
 
-template <int MAXS>
-__global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32)
+template <int MAXS, bool NOISE>
+__global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32, MAXS <= 4 ? 8 : 3)
 k_select(az_engine e, az_select_args a)
 {
     __shared__ uint32_t smask_all[AZ_WARPS_PER_CTA][64];
@@ -147,44 +227,9 @@ k_select(az_engine e, az_select_args a)
             // integers: exact in any order.
             const float sq = __fsqrt_rn((float)__reduce_add_sync(AZ_FULL, ni));
             float noise[MAXS];
-            if (depth == 0 && a.noise_scale != 0.0) {
-                // Dirichlet(alpha) over the root's children, redrawn at every
-                // simulation (mcts.py:105-114,126-131): gamma(alpha) samples
-                // by Marsaglia-Tsang on alpha+1 times U^(1/alpha), in logs.
-                const float alpha = (float)a.noise_alpha, aa = alpha + 1.0f;
-                const float d = aa - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
-                float lg[MAXS], mx = -INFINITY;
-#pragma unroll
-                for (int s = 0; s < MAXS; s++) {
-                    int j = lane + 32 * s;
-                    lg[s] = -INFINITY;
-                    if (j < k) {
-                        float r = logf(d);
-                        for (int att = 0; att < 16; att++) {
-                            uint4 u = az_philox(make_uint4((uint32_t)(sim0 + b), (uint32_t)j,
-                                                           (uint32_t)ply, 0xD1C10000u + att), key);
-                            float u1 = az_u01(u.x), u2 = az_u01(u.y), u3 = az_u01(u.z), u4 = az_u01(u.w);
-                            float nx = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-                            float v = 1.0f + c * nx;
-                            if (v <= 0.0f) continue;
-                            v = v * v * v;
-                            if (logf(u3) < 0.5f * nx * nx + d - d * v + d * logf(v)) {
-                                r = logf(d * v) + logf(u4) / alpha;
-                                break;
-                            }
-                        }
-                        lg[s] = r;
-                        mx = fmaxf(mx, r);
-                    }
-                }
-                for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AZ_FULL, mx, off));
-                float z = 0.0f;
-#pragma unroll
-                for (int s = 0; s < MAXS; s++) { lg[s] = expf(lg[s] - mx); z += lg[s]; }
-                for (int off = 16; off; off >>= 1) z += __shfl_xor_sync(AZ_FULL, z, off);
-#pragma unroll
-                for (int s = 0; s < MAXS; s++) noise[s] = lg[s] / z;
-            }
+            if (NOISE && depth == 0)
+                az_dirichlet_noise<MAXS>(k, (float)a.noise_alpha, (uint32_t)(sim0 + b),
+                                         (uint32_t)ply, key, noise);
             uint32_t bestkey = 0;
             int bestj = 0x7fffffff;
 #pragma unroll
@@ -193,7 +238,7 @@ k_select(az_engine e, az_select_args a)
                 if (j < k) {
                     float nv = __uint_as_float(rec[s].x), tv = __uint_as_float(rec[s].y);
                     float pr = __uint_as_float(rec[s].z);
-                    if (depth == 0 && a.noise_scale != 0.0)
+                    if (NOISE && depth == 0)    // mcts.py:128-131, mixed in float64
                         pr = (float)((1.0 - a.noise_scale) * (double)pr +
                                      a.noise_scale * (double)noise[s]);
                     float gap = __fdiv_rn(sq, __fadd_rn(1.0f, nv));

@@ -199,6 +199,14 @@ class Engine:
         """Device stub evaluator (test/bench aid) -> engine value/prior."""
         check(self.lib.az_stub_eval(self._h, int(mode), self._stream))
 
+    def noise_sample(self, alpha, k, sim=0):
+        """Test aid: the Dirichlet(alpha) root-noise vector each game would
+        draw for simulation `sim` of its current ply, f32[G, k]."""
+        out = self._new(self.num_games, k, dtype=torch.float32)
+        check(self.lib.az_noise_sample(self._h, float(alpha), int(k), int(sim),
+                                       _ptr(out), self._stream))
+        return out
+
     # ------------------------------------------------------ lockstep play --
     def play_commit(self, temperature=1.0, exploration_depth=15,
                     move_sampling=True, collect_replay=False, auto_reset=True,
@@ -228,6 +236,11 @@ class Engine:
         count = min(self.replay_count(), self.replay.shape[0])
         rows = self.replay[:count].cpu().numpy()
         self.replay_clear()
+        # finished games append in warp-scheduling order: sort by
+        # (game id, ply) so the output is deterministic
+        if len(rows):
+            key = rows[:, :12].copy().view([('g', '<i8'), ('p', '<i4')]).reshape(-1)
+            rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
         return rows
 
 

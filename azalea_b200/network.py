@@ -9,9 +9,11 @@ this module can be dropped into the reference's ``Policy``.  Two ways in:
 * ``evaluate_cells``: the lockstep path.  Takes the int8 network-view boards
   the select kernel wrote ([N, cell_stride]) and returns fp32 value [N] and
   fp32 logits over all n*n tiles [N, n*n]; BatchNorm is folded into the
-  convolutions, activations are bf16 channels-last.  Gathering the legal
-  tiles and the masked softmax happen in the expand kernel
-  (AZ_PRIOR_LOGITS), not here.
+  convolutions, activations are bf16 channels-last, and on CUDA every
+  convolution is one cuDNN call with bias, ReLU and the residual add in its
+  epilogue (2.8x over separate conv / bias / add / relu kernels on B200,
+  profiles/r01_nn_variants.txt).  Gathering the legal tiles and the masked
+  softmax happen in the expand kernel (AZ_PRIOR_LOGITS), not here.
 
 The network is the only dense contraction on the path and stays a PyTorch
 (cuDNN / cuBLAS) call by design; the tree kernels around it are ours.
@@ -127,16 +129,36 @@ class HexNetwork(nn.Module):
     # ------------------------------------------------------- lockstep path --
     @torch.no_grad()
     def prepare_inference(self, dtype=torch.bfloat16):
-        """Fold BatchNorm into the convolutions and cast for inference."""
+        """Fold BatchNorm into the convolutions and cast for inference.
+
+        Calling it again after the parameters changed refreshes the folded
+        tensors IN PLACE (same device addresses), so a captured CUDA graph
+        keeps reading the current weights."""
         assert not self.training, 'call .eval() first'
         dev = self.device
+        old = self._fast if (self._fast is not None
+                             and self._fast['dtype'] == dtype
+                             and self._fast['emb'].device == dev) else None
+        slot = [0]
+
+        def keep(t, channels_last=False):
+            t = t.to(dev, dtype)
+            t = t.contiguous(memory_format=torch.channels_last) \
+                if channels_last else t.contiguous()
+            if old is not None:
+                dst = old['_flat'][slot[0]]
+                dst.copy_(t)
+                t = dst
+            slot[0] += 1
+            flat.append(t)
+            return t
 
         def pack(w, b):
-            return (w.to(dev, dtype).contiguous(memory_format=torch.channels_last),
-                    b.to(dev, dtype).contiguous())
+            return keep(w, True), keep(b)
 
-        fast = {'dtype': dtype}
-        fast['emb'] = self.encoder.weight.to(dev, dtype).contiguous()
+        flat = []
+        fast = {'dtype': dtype, '_flat': flat}
+        fast['emb'] = keep(self.encoder.weight)
         fast['stem'] = pack(*_fold(self.conv1, self.bn1))
         fast['blocks'] = [(pack(*_fold(b.conv1, b.bn1)),
                            pack(*_fold(b.conv2, b.bn2)))
@@ -146,12 +168,9 @@ class HexNetwork(nn.Module):
         wp, bp = _fold(self.move_conv1, self.move_bn1)
         fast['heads'] = pack(torch.cat([wv, wp]), torch.cat([bv, bp]))
         fast['nv'] = wv.shape[0]
-        fast['value_fc2'] = (self.value_fc2.weight.to(dev, dtype),
-                             self.value_fc2.bias.to(dev, dtype))
-        fast['value_fc3'] = (self.value_fc3.weight.to(dev, dtype),
-                             self.value_fc3.bias.to(dev, dtype))
-        fast['move_fc'] = (self.move_fc.weight.to(dev, dtype),
-                           self.move_fc.bias.to(dev, dtype))
+        fast['value_fc2'] = (keep(self.value_fc2.weight), keep(self.value_fc2.bias))
+        fast['value_fc3'] = (keep(self.value_fc3.weight), keep(self.value_fc3.bias))
+        fast['move_fc'] = (keep(self.move_fc.weight), keep(self.move_fc.bias))
         self._fast = fast
         return self
 
@@ -167,12 +186,21 @@ class HexNetwork(nn.Module):
         idx = cells[:, :n * n].to(torch.int32)
         # [N, n, n, 4] in memory == channels-last [N, 4, n, n]
         x = F.embedding(idx, f['emb']).view(N, n, n, 4).permute(0, 3, 1, 2)
-        x = F.relu_(F.conv2d(x, *f['stem'], padding=1))
-        for (w1, b1), (w2, b2) in f['blocks']:
-            y = F.relu_(F.conv2d(x, w1, b1, padding=1))
-            y = F.conv2d(y, w2, b2, padding=1)
-            x = F.relu_(y.add_(x))
-        h = F.relu_(F.conv2d(x, *f['heads']))
+        if x.is_cuda and f['dtype'] != torch.float32:
+            one, pad, nopad = (1, 1), (1, 1), (0, 0)
+            x = torch.cudnn_convolution_relu(x, *f['stem'], one, pad, one, 1)
+            for (w1, b1), (w2, b2) in f['blocks']:
+                y = torch.cudnn_convolution_relu(x, w1, b1, one, pad, one, 1)
+                x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one,
+                                                     pad, one, 1)
+            h = torch.cudnn_convolution_relu(x, *f['heads'], one, nopad, one, 1)
+        else:
+            x = F.relu_(F.conv2d(x, *f['stem'], padding=1))
+            for (w1, b1), (w2, b2) in f['blocks']:
+                y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+                y = F.conv2d(y, w2, b2, padding=1)
+                x = F.relu_(y.add_(x))
+            h = F.relu_(F.conv2d(x, *f['heads']))
         nv = f['nv']
         v = F.relu_(F.linear(h[:, :nv].flatten(1), *f['value_fc2']))
         value = torch.tanh(F.linear(v, *f['value_fc3'])).squeeze(1)

@@ -119,22 +119,19 @@ class LockstepSelfPlay:
         eng.play_commit(self.temperature, self.depth, self.move_sampling,
                         self.collect_replay, True, self.chosen)
 
-    def capture(self, warmup=2):
-        """Warm up eagerly (cuDNN autotune), then capture one move as a
-        CUDA graph."""
-        for _ in range(warmup):
-            self._move_body()
-            self.moves_done += 1
+    def capture(self):
+        """Capture one move as a CUDA graph (capturing does not execute)."""
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             self._move_body()
-        self.moves_done += 1
         self._graph = graph
 
     def step_move(self):
-        """One move of every game (enqueue only; no host sync)."""
-        if self._want_graph and self._graph is None:
+        """One move of every game (enqueue only; no host sync).  The first
+        two moves run eagerly (cuDNN autotune, allocator warm-up), the third
+        call captures the move as a CUDA graph, later calls replay it."""
+        if self._want_graph and self._graph is None and self.moves_done >= 2:
             self.capture()
         if self._graph is not None:
             self._graph.replay()

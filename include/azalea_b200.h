@@ -211,6 +211,13 @@ int az_status(az_engine *e, int32_t *status_dev, void *stream);
  * AZ_BUF_PRIOR (AZ_PRIOR_PROBS layout) for the current leaves. */
 int az_stub_eval(az_engine *e, int mode, void *stream);
 
+/* Test aid for the root exploration noise (mcts.py:126-131), which only has
+ * statistical parity with RandomState.dirichlet: writes the Dirichlet(alpha)
+ * vector over k children that game g would draw for simulation `sim` of its
+ * current ply into out_dev f32[G][k]. */
+int az_noise_sample(az_engine *e, float alpha, int k, int sim, float *out_dev,
+                    void *stream);
+
 /* --------------------------------------------------------- lockstep play */
 
 typedef struct az_play_params {

@@ -288,3 +288,33 @@ def test_dirichlet_noise_statistics():
     assert (eng.status().cpu().numpy() == 0).all()
     # different games draw different noise
     assert len({v[g].tobytes() for g in range(G)}) > G // 2
+
+
+@pytest.mark.parametrize('alpha,k', ((0.03, 121), (0.3, 50), (1.0, 20), (2.5, 361)))
+def test_dirichlet_noise_distribution(alpha, k):
+    """The device noise has Dirichlet(alpha) statistics (what
+    RandomState.dirichlet(np.full(k, alpha)) gives, mcts.py:126-127): rows
+    sum to 1, component mean 1/k, component variance (k-1)/(k^2 (k alpha+1)),
+    and the distribution of the largest component matches NumPy's."""
+    from azalea_b200 import Engine
+    G = 4096
+    eng = Engine(G, 19, max_batch=1, nodes_per_game=4, seed=11)
+    draws = np.concatenate([eng.noise_sample(alpha, k, sim=s).cpu().numpy()
+                            for s in range(8)]).astype(np.float64)
+    assert np.allclose(draws.sum(1), 1.0, atol=1e-4)
+    assert (draws >= 0).all()
+    n = draws.size
+    mean, var = draws.mean(), draws.var()
+    want_var = (k - 1) / (k * k * (k * alpha + 1))
+    assert abs(mean - 1 / k) < 1e-6
+    assert abs(var / want_var - 1) < 0.05, (var, want_var)
+    ref = np.random.RandomState(0).dirichlet(np.full(k, alpha), size=len(draws))
+    q = [0.1, 0.25, 0.5, 0.75, 0.9]
+    got_q = np.quantile(draws.max(1), q)
+    ref_q = np.quantile(ref.max(1), q)
+    assert np.abs(got_q - ref_q).max() < 0.02, (got_q, ref_q)
+    # per-component marginal: a small-alpha Dirichlet is mostly tiny values
+    small = 1e-6
+    assert abs((draws < small).mean() - (ref < small).mean()) < 0.01
+    # different simulations and different games draw different vectors
+    assert len({draws[i].tobytes() for i in range(0, len(draws), 97)}) > 300

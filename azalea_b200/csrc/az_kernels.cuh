@@ -225,7 +225,9 @@ k_select(az_engine e, az_select_args a)
             }
             // score_actions, mcts.py:119-136.  sum(N) is a sum of small
             // integers: exact in any order.
-            const float sq = __fsqrt_rn((float)__reduce_add_sync(AZ_FULL, ni));
+            const int sum_n = __reduce_add_sync(AZ_FULL, ni);
+            const float sq = __fsqrt_rn((float)sum_n);
+            const bool sq_zero = sum_n == 0;
             float noise[MAXS];
             if (NOISE && depth == 0)
                 az_dirichlet_noise<MAXS>(k, (float)a.noise_alpha, (uint32_t)(sim0 + b),
@@ -241,9 +243,16 @@ k_select(az_engine e, az_select_args a)
                     if (NOISE && depth == 0)    // mcts.py:128-131, mixed in float64
                         pr = (float)((1.0 - a.noise_scale) * (double)pr +
                                      a.noise_scale * (double)noise[s]);
-                    float gap = __fdiv_rn(sq, __fadd_rn(1.0f, nv));
+                    // A zero numerator sends the IEEE division down its slow
+                    // subroutine (FCHK), and most children are unvisited
+                    // (W = 0) or the node is fresh (sum N = 0).  0/x = +-0 and
+                    // (+-0) + u == u for u >= +0, so those quotients are
+                    // replaced by 0 without changing a single bit of the score.
+                    float gap = sq_zero ? 0.0f : __fdiv_rn(sq, __fadd_rn(1.0f, nv));
                     float u = __fmul_rn(__fmul_rn(a.coef, pr), gap);
-                    float q = __fdiv_rn(-tv, fmaxf(nv, 1.0f));
+                    const bool tv_zero = tv == 0.0f;
+                    float q = __fdiv_rn(tv_zero ? 1.0f : -tv, fmaxf(nv, 1.0f));
+                    q = tv_zero ? 0.0f : q;
                     // + 0.0f folds -0 into +0 so the integer key orders like floats
                     uint32_t sk = az_orderable(__fadd_rn(__fadd_rn(q, u), 0.0f));
                     if (bestj == 0x7fffffff || sk > bestkey) { bestkey = sk; bestj = j; }

@@ -229,34 +229,50 @@ k_select(az_engine e, az_select_args a)
             const float sq = __fsqrt_rn((float)sum_n);
             const bool sq_zero = sum_n == 0;
             float noise[MAXS];
+            uint32_t bestkey = 0;
+            int bestj = 0x7fffffff;
+            // sum N == 0 (first descent into a freshly expanded node): every
+            // score is (c*P)*0 = +0, and np.argmax takes child 0 whatever the
+            // priors are -- nothing to compute.
+            if (sq_zero) {
+                bestj = lane == 0 ? 0 : 0x7fffffff;
+            } else {
             if (NOISE && depth == 0)
                 az_dirichlet_noise<MAXS>(k, (float)a.noise_alpha, (uint32_t)(sim0 + b),
                                          (uint32_t)ply, key, noise);
-            uint32_t bestkey = 0;
-            int bestj = 0x7fffffff;
 #pragma unroll
             for (int s = 0; s < MAXS; s++) {
-                int j = lane + 32 * s;
-                if (j < k) {
-                    float nv = __uint_as_float(rec[s].x), tv = __uint_as_float(rec[s].y);
-                    float pr = __uint_as_float(rec[s].z);
-                    if (NOISE && depth == 0)    // mcts.py:128-131, mixed in float64
-                        pr = (float)((1.0 - a.noise_scale) * (double)pr +
-                                     a.noise_scale * (double)noise[s]);
+                const int j = lane + 32 * s;
+                const float nv = __uint_as_float(rec[s].x), tv = __uint_as_float(rec[s].y);
+                float pr = __uint_as_float(rec[s].z);
+                if (NOISE && depth == 0)    // mcts.py:128-131, mixed in float64
+                    pr = (float)((1.0 - a.noise_scale) * (double)pr +
+                                 a.noise_scale * (double)noise[s]);
+                const float cp = __fmul_rn(a.coef, pr);
+                float score;
+                // Warp-uniform shortcut: if none of these 32 children has been
+                // visited, N = W = 0 for all of them, so Q = -0/1 and the visit
+                // gap is sqrt(sum N)/1: no division needed.  Most nodes below the
+                // root are in this state for most of their slots.
+                if (__any_sync(AZ_FULL, nv != 0.0f)) {
                     // A zero numerator sends the IEEE division down its slow
-                    // subroutine (FCHK), and most children are unvisited
-                    // (W = 0) or the node is fresh (sum N = 0).  0/x = +-0 and
-                    // (+-0) + u == u for u >= +0, so those quotients are
-                    // replaced by 0 without changing a single bit of the score.
-                    float gap = sq_zero ? 0.0f : __fdiv_rn(sq, __fadd_rn(1.0f, nv));
-                    float u = __fmul_rn(__fmul_rn(a.coef, pr), gap);
+                    // subroutine (FCHK).  0/x = +-0 and (+-0) + u == u for
+                    // u >= +0, so those quotients are replaced by an exact 0
+                    // without changing a bit of the score.
+                    const float gap = __fdiv_rn(sq, __fadd_rn(1.0f, nv));
                     const bool tv_zero = tv == 0.0f;
                     float q = __fdiv_rn(tv_zero ? 1.0f : -tv, fmaxf(nv, 1.0f));
                     q = tv_zero ? 0.0f : q;
+                    score = __fadd_rn(q, __fmul_rn(cp, gap));
+                } else {
+                    score = __fmul_rn(cp, sq);
+                }
+                if (j < k) {
                     // + 0.0f folds -0 into +0 so the integer key orders like floats
-                    uint32_t sk = az_orderable(__fadd_rn(__fadd_rn(q, u), 0.0f));
+                    const uint32_t sk = az_orderable(__fadd_rn(score, 0.0f));
                     if (bestj == 0x7fffffff || sk > bestkey) { bestkey = sk; bestj = j; }
                 }
+            }
             }
             // np.argmax: the lowest index among equal maxima (mcts.py:112)
             const uint32_t mxkey = __reduce_max_sync(AZ_FULL, bestkey);

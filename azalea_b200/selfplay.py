@@ -140,9 +140,26 @@ class LockstepSelfPlay:
         self.moves_done += 1
 
     # -------------------------------------------------------------- output --
-    def harvest(self):
-        """Finished games' replay rows (host, raw uint8 [R, row_bytes])."""
-        return self.eng.harvest_replay()
+    def harvest(self, gather=False):
+        """Finished games' replay rows (host, raw uint8 [R, row_bytes]).
+
+        With ``gather=True`` under torch.distributed, every rank's rows are
+        gathered to rank 0 over NCCL (the path's only exchange):
+        rank 0 returns all rows, the other ranks an empty array."""
+        if not gather:
+            return self.eng.harvest_replay()
+        import torch.distributed as dist
+        eng = self.eng
+        count = min(eng.replay_count(), eng.replay.shape[0])
+        rows = gather_replay_rows(eng.replay[:count])
+        eng.replay_clear()
+        if rows is None or (dist.is_initialized() and dist.get_rank() != 0):
+            return np.zeros((0, eng.row_bytes), dtype=np.uint8)
+        rows = rows.cpu().numpy()
+        if len(rows):
+            key = rows[:, :12].copy().view([('g', '<i8'), ('p', '<i4')]).reshape(-1)
+            rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
+        return rows
 
     def counters(self):
         return self.eng.counter_totals()

@@ -345,7 +345,7 @@ def run_ours(args):
             h2d += h2d_step
         sp.step_move()
         chosen_host.copy_(sp.chosen, non_blocking=True)
-        rows = sp.harvest()                 # syncs; D2H of finished games' rows
+        rows = sp.harvest(gather=world > 1)  # syncs; D2H of finished games' rows (rank 0 gets all)
         rows_out += len(rows)
         d2h += chosen_host.numel() * 4 + rows.nbytes + 8
     barrier()

@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include "az_kernels.cuh"
+#include "az_nn_glue.cuh"
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -841,6 +842,45 @@ int az_noise_sample(az_engine *e, float alpha, int k, int sim, float *out_dev, v
 {
     if (!e || !out_dev || k < 1 || k > e->nn || alpha <= 0.0f) return AZ_E_INVALID;
     AZ_LAUNCH(k_noise_sample, e, stream, alpha, k, sim, out_dev);
+}
+
+int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t num_boards,
+               const void *table_dev, const float *bias_dev, void *out_dev, int channels,
+               void *stream)
+{
+    if (!cells_dev || !table_dev || !bias_dev || !out_dev || board_size < 2 || board_size > 19 ||
+        channels < 8 || channels > AZ_NN_MAXC || (channels & 7) || num_boards < 0 ||
+        cell_stride < board_size * board_size)
+        return AZ_E_INVALID;
+    if (num_boards == 0) return AZ_OK;
+    const int pnn = (board_size + 2) * (board_size + 2);
+    const int nn = board_size * board_size;
+    const size_t smem = (size_t)36 * channels * 2 + (size_t)((nn + 1) & ~1) * 2 +
+                        (size_t)AZ_NN_STEM_BOARDS * pnn;
+    if (256 % (channels >> 3)) return AZ_E_UNSUPPORTED;
+    long long blocks = (num_boards + AZ_NN_STEM_BOARDS - 1) / AZ_NN_STEM_BOARDS;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_nn_stem<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+        cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
+        bias_dev, (uint16_t *)out_dev, channels);
+    return az_check(cudaGetLastError());
+}
+
+int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const float *b_dev,
+                void *out_dev, int channels, int heads, void *stream)
+{
+    if (!x_dev || !w_dev || !b_dev || !out_dev || channels < 8 || channels > AZ_NN_MAXC ||
+        (channels & 7) || positions < 0)
+        return AZ_E_INVALID;
+    if (heads != 6) return AZ_E_UNSUPPORTED;   /* value_chans 2 + policy_chans 4, network.py:123 */
+    if (((channels >> 3) & ((channels >> 3) - 1)) || (channels >> 3) < 4)
+        return AZ_E_UNSUPPORTED;               /* lanes per position: power of two, >= heads/2 */
+    if (positions == 0) return AZ_OK;
+    long long blocks = (positions * (channels >> 3) + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_nn_heads<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t *)x_dev, (long long)positions, w_dev, b_dev, (uint16_t *)out_dev, channels);
+    return az_check(cudaGetLastError());
 }
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)

@@ -1,0 +1,160 @@
+// az_nn_glue.cuh -- the evaluator's input and output glue (sm_100a).
+//
+// The 6x64 tower itself stays a library call (cuDNN, by design); these are
+// the two ends of it that the library runs badly (profiles/r01_nn_launches):
+//
+//  k_nn_stem   network.py:138-142 + :71  Embedding(3,4) -> conv3x3(4->C) -> BN
+//              -> ReLU.  A cell has 3 possible values, so the whole thing is a
+//              table: out[p][c] = relu(bias[c] + sum_tap T[tap][cell(p+tap)][c])
+//              with T = conv weights x embedding, BN folded.  Reads the int8
+//              boards k_select wrote, writes bf16 NHWC activations.  HBM-bound:
+//              n*n*C*2 bytes written per board (cuDNN: 0.81 ms, a K=36 GEMM
+//              through a legacy kernel plus a channel-padding pass).
+//  k_nn_heads  network.py:75-76,82-83  both 1x1 head convolutions (C -> 2 + 4)
+//              + BN + ReLU in one pass over the tower output.  HBM-bound:
+//              n*n*C*2 bytes read per board (library: 0.53 ms for an N=6 GEMM).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define AZ_NN_MAXC 128
+#define AZ_NN_STEM_BOARDS 4
+
+__device__ __forceinline__ void az_bf16x8_to_f32(const uint4 &v, float (&f)[8])
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+
+__device__ __forceinline__ uint32_t az_pack_bf16x2(float lo, float hi)
+{
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&p);
+}
+
+// table: bf16 [9][4][C] (tap-major; value 3 = off board = zeros), bias f32 [C].
+// Thread = (position lane, channel group of 8): 256 threads = (256 / groups)
+// positions x groups.  Table and a per-position offset list live in shared
+// memory, so the inner loop is 9 x (1 byte LDS + 16 B LDS + unpack + 8 FADD).
+__global__ void __launch_bounds__(256)
+k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
+          const uint16_t *__restrict__ table, const float *__restrict__ bias,
+          uint16_t *__restrict__ out, int C)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t *stab = reinterpret_cast<uint16_t *>(smem_raw);                 // 36*C bf16
+    uint16_t *spos = reinterpret_cast<uint16_t *>(smem_raw + 36 * C * 2);     // nn offsets (padded to even)
+    const int nn = n * n, pn = n + 2, pnn = pn * pn;
+    int8_t *scell = reinterpret_cast<int8_t *>(smem_raw + 36 * C * 2 + ((nn + 1) & ~1) * 2);
+    const int groups = C >> 3;
+    const int cg = threadIdx.x % groups, tp = threadIdx.x / groups, ppt = blockDim.x / groups;
+    for (int i = threadIdx.x; i < 36 * C; i += blockDim.x) stab[i] = table[i];
+    for (int i = threadIdx.x; i < nn; i += blockDim.x)
+        spos[i] = (uint16_t)((i / n) * pn + (i % n));       // top-left neighbour in the padded board
+    float b8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) b8[k] = bias[cg * 8 + k];
+    const uint16_t *trow = stab + cg * 8;
+    for (long long b0 = (long long)blockIdx.x * AZ_NN_STEM_BOARDS; b0 < N;
+         b0 += (long long)gridDim.x * AZ_NN_STEM_BOARDS) {
+        __syncthreads();
+        // stage the boards with a border of "off board" cells
+        for (int i = threadIdx.x; i < AZ_NN_STEM_BOARDS * pnn; i += blockDim.x) {
+            const int q = i / pnn, r = (i % pnn) / pn - 1, c = (i % pnn) % pn - 1;
+            int8_t v = 3;
+            if (b0 + q < N && r >= 0 && r < n && c >= 0 && c < n)
+                v = cells[(b0 + q) * cell_stride + r * n + c];
+            scell[i] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int q = 0; q < AZ_NN_STEM_BOARDS; q++) {
+            if (b0 + q >= N) break;
+            uint16_t *orow = out + (b0 + q) * (long long)nn * C + cg * 8;
+            for (int p = tp; p < nn; p += ppt) {
+                const int8_t *sc = scell + q * pnn + spos[p];
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = b8[k];
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) {
+                    const int v = sc[(tap / 3) * pn + (tap % 3)];
+                    const uint4 t = *reinterpret_cast<const uint4 *>(trow + (tap * 4 + v) * C);
+                    float f[8];
+                    az_bf16x8_to_f32(t, f);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] += f[k];
+                }
+                uint4 o;
+                o.x = az_pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+                o.y = az_pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+                o.z = az_pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+                o.w = az_pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+                *reinterpret_cast<uint4 *>(orow + (long long)p * C) = o;
+            }
+        }
+    }
+}
+
+// x: bf16 [P][C] (NHWC positions), w: f32 [H][C], b: f32 [H], out: bf16 [P][H].
+// `groups` = C/8 lanes share a position: each lane loads one 16-byte slice
+// (fully coalesced), keeps its 8 x H weights in registers, and the partial
+// dot products are summed across the group by xor-shuffles.  groups must be
+// a power of two <= 32 (C in {8,16,32,64,128,256}); H even.
+template <int H>
+__global__ void __launch_bounds__(256)
+k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict__ w,
+           const float *__restrict__ b, uint16_t *__restrict__ out, int C)
+{
+    const int groups = C >> 3;
+    const int lane = threadIdx.x & 31, cg = lane % groups, sub = lane / groups;
+    const int ppw = 32 / groups;                        // positions per warp per step
+    float wr[H][8], br[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        br[h] = b[h];
+#pragma unroll
+        for (int k = 0; k < 8; k++) wr[h][k] = w[h * C + cg * 8 + k];
+    }
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;                                // independent loads in flight per lane
+    for (long long p0 = warp * ppw * U; p0 < P; p0 += nwarps * ppw * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long p = p0 + u * ppw + sub;
+            v[u] = p < P ? *reinterpret_cast<const uint4 *>(x + p * C + cg * 8) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const long long p = p0 + u * ppw + sub;
+            float f[8], acc[H];
+            az_bf16x8_to_f32(v[u], f);
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                acc[h] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[h] = fmaf(f[k], wr[h][k], acc[h]);
+            }
+            for (int off = 1; off < groups; off <<= 1)
+#pragma unroll
+                for (int h = 0; h < H; h++) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], off);
+            if (p < P && cg < H / 2) {
+                // lane cg of the group writes outputs 2cg, 2cg+1
+                float lo = 0.f, hi = 0.f;
+#pragma unroll
+                for (int h = 0; h < H; h += 2)
+                    if (cg == h / 2) { lo = acc[h] + br[h]; hi = acc[h + 1] + br[h + 1]; }
+                reinterpret_cast<uint32_t *>(out + p * H)[cg] =
+                    az_pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+            }
+        }
+    }
+}

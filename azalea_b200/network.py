@@ -141,8 +141,8 @@ class HexNetwork(nn.Module):
                              and self._fast['emb'].device == dev) else None
         slot = [0]
 
-        def keep(t, channels_last=False):
-            t = t.to(dev, dtype)
+        def keep(t, channels_last=False, dtype_=None):
+            t = t.to(dev, dtype_ or dtype)
             t = t.contiguous(memory_format=torch.channels_last) \
                 if channels_last else t.contiguous()
             if old is not None:
@@ -153,24 +153,49 @@ class HexNetwork(nn.Module):
             flat.append(t)
             return t
 
+        def keep32(t):
+            return keep(t, dtype_=torch.float32)
+
         def pack(w, b):
             return keep(w, True), keep(b)
 
         flat = []
         fast = {'dtype': dtype, '_flat': flat}
         fast['emb'] = keep(self.encoder.weight)
-        fast['stem'] = pack(*_fold(self.conv1, self.bn1))
+        ws, bs = _fold(self.conv1, self.bn1)
+        fast['stem'] = pack(ws, bs)
+        # stem as a table for az_nn_stem: T[tap][cell value][c_out]
+        tab = torch.einsum('ocyx,vc->yxvo', ws.float(), self.encoder.weight.float())
+        tab = F.pad(tab, (0, 0, 0, 1)).reshape(9, 4, -1)
+        fast['stem_table'] = keep(tab)
+        fast['stem_bias'] = keep32(bs)
         fast['blocks'] = [(pack(*_fold(b.conv1, b.bn1)),
                            pack(*_fold(b.conv2, b.bn2)))
                           for b in self.resblocks]
-        # the two 1x1 head convolutions read the same activations: one conv
+        # the two 1x1 head convolutions read the same activations: one conv;
+        # the two first fully connected layers read its output: one GEMM over
+        # the channels-last flattening (hw-major, channel-minor), so no
+        # layout change is needed between the conv and the GEMM
         wv, bv = _fold(self.value_conv1, self.value_bn1)
         wp, bp = _fold(self.move_conv1, self.move_bn1)
         fast['heads'] = pack(torch.cat([wv, wp]), torch.cat([bv, bp]))
-        fast['nv'] = wv.shape[0]
-        fast['value_fc2'] = (keep(self.value_fc2.weight), keep(self.value_fc2.bias))
+        fast['heads_w32'] = keep32(torch.cat([wv, wp]).flatten(1))
+        fast['heads_b32'] = keep32(torch.cat([bv, bp]))
+        nv, npc = wv.shape[0], wp.shape[0]
+        hw = self.board_size ** 2
+        hc = nv + npc
+        w2, wm = self.value_fc2.weight, self.move_fc.weight
+        merged = torch.zeros(w2.shape[0] + wm.shape[0], hw * hc,
+                             dtype=w2.dtype, device=w2.device)
+        # reference flattening is channel-major: column c * hw + p
+        merged[:w2.shape[0]].view(-1, hw, hc)[:, :, :nv] = \
+            w2.view(-1, nv, hw).permute(0, 2, 1)
+        merged[w2.shape[0]:].view(-1, hw, hc)[:, :, nv:] = \
+            wm.view(-1, npc, hw).permute(0, 2, 1)
+        fast['fc'] = (keep(merged),
+                      keep(torch.cat([self.value_fc2.bias, self.move_fc.bias])))
+        fast['nfc2'] = w2.shape[0]
         fast['value_fc3'] = (keep(self.value_fc3.weight), keep(self.value_fc3.bias))
-        fast['move_fc'] = (keep(self.move_fc.weight), keep(self.move_fc.bias))
         self._fast = fast
         return self
 
@@ -183,17 +208,48 @@ class HexNetwork(nn.Module):
             raise RuntimeError('call prepare_inference() first')
         n = self.board_size
         N = cells.shape[0]
-        idx = cells[:, :n * n].to(torch.int32)
-        # [N, n, n, 4] in memory == channels-last [N, 4, n, n]
-        x = F.embedding(idx, f['emb']).view(N, n, n, 4).permute(0, 3, 1, 2)
+        C_ = f['stem_bias'].numel()
+        glue = (cells.is_cuda and f['dtype'] == torch.bfloat16
+                and C_ in (32, 64, 128) and cells.dtype == torch.int8
+                and cells.stride(1) == 1)
+        if glue:
+            # our kernels at both ends of the tower (csrc/az_nn_glue.cuh)
+            from . import _cabi
+            import ctypes
+            L = _cabi.lib()
+            stream = ctypes.c_void_p(torch.cuda.current_stream(cells.device).cuda_stream)
+            x = torch.empty(N, n, n, C_, dtype=torch.bfloat16, device=cells.device)
+            _cabi.check(L.az_nn_stem(
+                ctypes.c_void_p(cells.data_ptr()), cells.stride(0), n, N,
+                ctypes.c_void_p(f['stem_table'].data_ptr()),
+                ctypes.c_void_p(f['stem_bias'].data_ptr()),
+                ctypes.c_void_p(x.data_ptr()), C_, stream))
+            x = x.permute(0, 3, 1, 2)       # NCHW view of NHWC memory
+        else:
+            idx = cells[:, :n * n].to(torch.int32)
+            x = F.embedding(idx, f['emb']).view(N, n, n, 4).permute(0, 3, 1, 2)
         if x.is_cuda and f['dtype'] != torch.float32:
             one, pad, nopad = (1, 1), (1, 1), (0, 0)
-            x = torch.cudnn_convolution_relu(x, *f['stem'], one, pad, one, 1)
+            if not glue:
+                x = torch.cudnn_convolution_relu(x, *f['stem'], one, pad, one, 1)
             for (w1, b1), (w2, b2) in f['blocks']:
                 y = torch.cudnn_convolution_relu(x, w1, b1, one, pad, one, 1)
                 x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, one,
                                                      pad, one, 1)
-            h = torch.cudnn_convolution_relu(x, *f['heads'], one, nopad, one, 1)
+            if glue:
+                xh = x.permute(0, 2, 3, 1)
+                if not xh.is_contiguous():
+                    xh = xh.contiguous()
+                flat = torch.empty(N, n * n * 6, dtype=torch.bfloat16,
+                                   device=cells.device)
+                _cabi.check(L.az_nn_heads(
+                    ctypes.c_void_p(xh.data_ptr()), N * n * n,
+                    ctypes.c_void_p(f['heads_w32'].data_ptr()),
+                    ctypes.c_void_p(f['heads_b32'].data_ptr()),
+                    ctypes.c_void_p(flat.data_ptr()), C_, 6, stream))
+                h = None
+            else:
+                h = torch.cudnn_convolution_relu(x, *f['heads'], one, nopad, one, 1)
         else:
             x = F.relu_(F.conv2d(x, *f['stem'], padding=1))
             for (w1, b1), (w2, b2) in f['blocks']:
@@ -201,8 +257,11 @@ class HexNetwork(nn.Module):
                 y = F.conv2d(y, w2, b2, padding=1)
                 x = F.relu_(y.add_(x))
             h = F.relu_(F.conv2d(x, *f['heads']))
-        nv = f['nv']
-        v = F.relu_(F.linear(h[:, :nv].flatten(1), *f['value_fc2']))
-        value = torch.tanh(F.linear(v, *f['value_fc3'])).squeeze(1)
-        logits = F.linear(h[:, nv:].flatten(1), *f['move_fc'])
+        # [N, C, n, n] channels-last == [N, n*n*C] row-major: free view
+        if h is not None:
+            flat = h.permute(0, 2, 3, 1).reshape(N, -1)
+        y = F.linear(flat, *f['fc'])
+        k2 = f['nfc2']
+        value = torch.tanh(F.linear(F.relu(y[:, :k2]), *f['value_fc3'])).squeeze(1)
+        logits = y[:, k2:]
         return value.float(), logits.float()

@@ -211,6 +211,24 @@ int az_status(az_engine *e, int32_t *status_dev, void *stream);
  * AZ_BUF_PRIOR (AZ_PRIOR_PROBS layout) for the current leaves. */
 int az_stub_eval(az_engine *e, int mode, void *stream);
 
+/* ------------------------------------------------------- evaluator glue */
+
+/* HexNetwork input stage (network.py:138-142 + :71): Embedding(3,4) ->
+ * conv3x3(4 -> channels) -> BatchNorm -> ReLU as one table lookup kernel.
+ * cells int8 [num_boards][cell_stride] (network-view 0/1/2, what
+ * az_mcts_select wrote), table bf16 [9][4][channels] = conv weights x
+ * embedding with BN folded (row 3 of each tap = zeros = off board), bias
+ * f32 [channels]; out bf16 [num_boards][n*n][channels] (NHWC). */
+int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size,
+               int64_t num_boards, const void *table_dev, const float *bias_dev,
+               void *out_dev, int channels, void *stream);
+/* Both 1x1 head convolutions + BN + ReLU (network.py:75-76,82-83) in one
+ * pass: x bf16 [positions][channels] (NHWC), w f32 [heads][channels], b f32
+ * [heads] -> out bf16 [positions][heads]; heads = 6 (2 value + 4 policy). */
+int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev,
+                const float *b_dev, void *out_dev, int channels, int heads,
+                void *stream);
+
 /* Test aid for the root exploration noise (mcts.py:126-131), which only has
  * statistical parity with RandomState.dirichlet: writes the Dirichlet(alpha)
  * vector over k children that game g would draw for simulation `sim` of its

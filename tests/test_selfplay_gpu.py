@@ -219,3 +219,63 @@ def test_player_facade():
     assert len(df) >= 200
     assert metrics['games'] > 0 and metrics['game_error'] == 0
     assert 5 <= metrics['moves_per_game'] / metrics['games'] <= 25
+
+
+@pytest.mark.parametrize('n,chans', ((11, 64), (7, 32), (19, 64)))
+def test_evaluator_glue_kernels_match_torch(n, chans):
+    """az_nn_stem / az_nn_heads (csrc/az_nn_glue.cuh) against plain PyTorch
+    fp32 of the same layers (network.py:68-85,138-142): one bf16 rounding of
+    the output is the only difference allowed (rel 2^-8 + abs 1e-3)."""
+    import ctypes
+    import torch.nn.functional as F
+    from azalea_b200 import _cabi
+    from azalea_b200.network import HexNetwork, _fold
+    torch.manual_seed(n)
+    net = HexNetwork(n, 2, chans).eval().cuda()
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen, device='cuda') * 0.2)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen, device='cuda') + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=gen, device='cuda') + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=gen, device='cuda') * 0.2)
+    net.prepare_inference(torch.bfloat16)
+    f = net._fast
+    N, nn = 257, n * n
+    cs = (nn + 15) & ~15
+    cells = torch.zeros(N, cs, dtype=torch.int8, device='cuda')
+    cells[:, :nn] = torch.randint(0, 3, (N, nn), device='cuda', dtype=torch.int8)
+    L = _cabi.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # stem
+    out = torch.empty(N, n, n, chans, dtype=torch.bfloat16, device='cuda')
+    _cabi.check(L.az_nn_stem(ctypes.c_void_p(cells.data_ptr()), cs, n, N,
+                             ctypes.c_void_p(f['stem_table'].data_ptr()),
+                             ctypes.c_void_p(f['stem_bias'].data_ptr()),
+                             ctypes.c_void_p(out.data_ptr()), chans, stream))
+    with torch.no_grad():
+        x = net.encoder(cells[:, :nn].long().view(N, n, n)).permute(0, 3, 1, 2)
+        want = F.relu(net.bn1(net.conv1(x))).permute(0, 2, 3, 1)
+    got = out.float()
+    tol = want.abs() * 2 ** -6 + 2e-2       # table entries are bf16 too
+    assert ((got - want).abs() <= tol).all(), float((got - want).abs().max())
+    # heads
+    xin = (torch.randn(N * nn, chans, device='cuda') * 0.7).to(torch.bfloat16)
+    hout = torch.empty(N * nn, 6, dtype=torch.bfloat16, device='cuda')
+    _cabi.check(L.az_nn_heads(ctypes.c_void_p(xin.data_ptr()), N * nn,
+                              ctypes.c_void_p(f['heads_w32'].data_ptr()),
+                              ctypes.c_void_p(f['heads_b32'].data_ptr()),
+                              ctypes.c_void_p(hout.data_ptr()), chans, 6, stream))
+    want = F.relu(xin.float() @ f['heads_w32'].t() + f['heads_b32'])
+    got = hout.float()
+    assert ((got - want).abs() <= want.abs() * 2 ** -7 + 1e-3).all()
+    # whole evaluator: bf16 glue path vs the reference-interface fp32 path
+    value, logits = net.evaluate_cells(cells)
+    with torch.no_grad():
+        moves = torch.arange(1, nn + 1, device='cuda', dtype=torch.int32).repeat(N, 1)
+        ref = net.run(dict(board=cells[:, :nn].view(N, n, n).int(), legal_moves=moves))
+    assert (value - ref['value']).abs().max() < 0.05
+    want_lp = ref['moves_logprob']
+    got_lp = torch.log_softmax(logits, 1)
+    assert (got_lp - want_lp).abs().max() < 0.25
+    assert (got_lp - want_lp).abs().mean() < 0.02

@@ -25,20 +25,23 @@ def timeit(fn, reps=5):
 def base(c=cells):
     return net.evaluate_cells(c)
 
-def fused(c=cells):
+def unfused(c=cells):
+    """Separate conv / bias / add / relu kernels (what plain F.conv2d gives)."""
     n = 11; M = c.shape[0]
     idx = c[:, :121].to(torch.int32)
     x = F.embedding(idx, f['emb']).view(M, n, n, 4).permute(0, 3, 1, 2)
-    x = torch.cudnn_convolution_relu(x, f['stem'][0], f['stem'][1], (1, 1), (1, 1), (1, 1), 1)
+    x = F.relu_(F.conv2d(x, *f['stem'], padding=1))
     for (w1, b1), (w2, b2) in f['blocks']:
-        y = torch.cudnn_convolution_relu(x, w1, b1, (1, 1), (1, 1), (1, 1), 1)
-        x = torch.cudnn_convolution_add_relu(y, w2, x, 1.0, b2, (1, 1), (1, 1), (1, 1), 1)
-    h = torch.cudnn_convolution_relu(x, f['heads'][0], f['heads'][1], (1, 1), (0, 0), (1, 1), 1)
-    nv = f['nv']
-    v = F.relu_(F.linear(h[:, :nv].flatten(1), *f['value_fc2']))
-    value = torch.tanh(F.linear(v, *f['value_fc3'])).squeeze(1)
-    logits = F.linear(h[:, nv:].flatten(1), *f['move_fc'])
-    return value.float(), logits.float()
+        y = F.relu_(F.conv2d(x, w1, b1, padding=1))
+        y = F.conv2d(y, w2, b2, padding=1)
+        x = F.relu_(y.add_(x))
+    h = F.relu_(F.conv2d(x, *f['heads']))
+    flat = h.permute(0, 2, 3, 1).reshape(M, -1)
+    y = F.linear(flat, *f['fc'])
+    k2 = f['nfc2']
+    value = torch.tanh(F.linear(F.relu(y[:, :k2]), *f['value_fc3'])).squeeze(1)
+    return value.float(), y[:, k2:].float()
+
 
 def chunked(fn, chunk):
     def run():
@@ -49,7 +52,7 @@ def chunked(fn, chunk):
 flop = 107.852e6 * N
 res = {}
 v0, l0 = base()
-for name, fn in [('base', base), ('fused', fused)]:
+for name, fn in [('evaluate_cells', base), ('unfused', unfused)]:
     try:
         v, l = fn()
         err = (v - v0).abs().max().item(), (l - l0).abs().max().item()
@@ -58,7 +61,7 @@ for name, fn in [('base', base), ('fused', fused)]:
     except Exception as e:
         print(name, 'FAILED', repr(e)[:300], flush=True)
 for chunk in (2048, 4096, 8192, 16384):
-    for name, fn in [('base', base), ('fused', fused)]:
+    for name, fn in [('evaluate_cells', base), ('unfused', unfused)]:
         try:
             run = chunked(fn, chunk)
             ms = timeit(run)

@@ -9,12 +9,14 @@ of games per GPU.  There is no CPU fallback.
 from . import typing, utils
 from .azalea_agent import AzaleaAgent
 from .engine import Engine
+from .evaluation import evaluate, play_matches
 from .game.hex import HexGame
 from .parallel_player import Player
 from .play_game import play_game
 from .policy import Policy
 from .random_policy import RandomPolicy
 from .replay_buffer import ReplayDataFrame, ReplayRecord
+from .replay_device import DeviceReplayBuffer
 from .search_tree import SearchTree, SearchTreeFull, as_distribution
 from .selfplay import LockstepSelfPlay, StubEvaluator
 
@@ -22,4 +24,5 @@ __version__ = '0.1.0'
 __all__ = ['AzaleaAgent', 'Engine', 'HexGame', 'Player', 'play_game',
            'Policy', 'RandomPolicy', 'ReplayDataFrame', 'ReplayRecord',
            'SearchTree', 'SearchTreeFull', 'as_distribution',
-           'LockstepSelfPlay', 'StubEvaluator', 'typing', 'utils']
+           'LockstepSelfPlay', 'StubEvaluator', 'DeviceReplayBuffer', 'evaluate',
+           'play_matches', 'typing', 'utils']

@@ -99,6 +99,8 @@ def lib():
     L.az_tree_move.argtypes = [eng, i32p, vp]
     L.az_status.argtypes = [eng, i32p, vp]
     L.az_stub_eval.argtypes = [eng, C.c_int, vp]
+    L.az_replay_collate.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, i32p, i32p,
+                                    f32p, f32p, vp, vp, i32p, vp]
     L.az_nn_stem.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, f32p, vp, C.c_int, vp]
     L.az_nn_heads.argtypes = [vp, C.c_int64, f32p, f32p, vp, C.c_int, C.c_int, vp]
     L.az_noise_sample.argtypes = [eng, C.c_float, C.c_int, C.c_int, f32p, vp]

@@ -552,6 +552,71 @@ __global__ void k_replay_clear(az_engine e)
     if (threadIdx.x == 0 && blockIdx.x == 0) e.globals[0] = 0ull;
 }
 
+
+// ---------------------------------------------------------- replay collate
+
+// prep.torch_batch_replays (prep.py:24-39) for replay rows that never left
+// the device: one warp per sampled row -> padded training tensors.
+// pi = as_distribution(visits, temperature) (search_tree.py:327-344) in
+// float64, cast to float32.
+__global__ void k_replay_collate(const uint8_t *rows, int row_bytes, const int64_t *idx, int count,
+                                 int n, int cell_stride, int32_t *board, int32_t *moves,
+                                 float *probs, float *reward, int64_t *color, int64_t *result,
+                                 int32_t *num_moves)
+{
+    const int lane = az_lane();
+    const int i = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (i >= count) return;
+    const int nn = n * n;
+    const uint8_t *row = rows + (size_t)idx[i] * row_bytes;
+    const az_row_header h = *reinterpret_cast<const az_row_header *>(row);
+    const int8_t *cells = reinterpret_cast<const int8_t *>(row + sizeof(az_row_header));
+    const float *vis = reinterpret_cast<const float *>(row + sizeof(az_row_header) + cell_stride);
+    const int k = h.num_moves;
+    // distribution over the k legal moves
+    double tot = 0.0;
+    float mx = 0.0f;
+    for (int j = lane; j < k; j += 32) mx = fmaxf(mx, vis[j]);
+    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AZ_FULL, mx, off));
+    const double inv_t = h.temperature > 0.0f ? 1.0 / (double)h.temperature : 0.0;
+    for (int j = lane; j < k; j += 32) {
+        const float v = vis[j];
+        double w;
+        if (h.temperature > 0.0f) w = v > 0.0f ? (h.temperature == 1.0f ? (double)v : pow((double)v, inv_t)) : 0.0;
+        else w = v == mx ? 1.0 : 0.0;
+        tot += w;
+    }
+    for (int off = 16; off; off >>= 1) tot += __shfl_xor_sync(AZ_FULL, tot, off);
+    for (int j = lane; j < nn; j += 32) {
+        float p = 0.0f;
+        if (j < k) {
+            const float v = vis[j];
+            double w;
+            if (h.temperature > 0.0f) w = v > 0.0f ? (h.temperature == 1.0f ? (double)v : pow((double)v, inv_t)) : 0.0;
+            else w = v == mx ? 1.0 : 0.0;
+            p = (float)(w / tot);
+        }
+        probs[(size_t)i * nn + j] = p;
+    }
+    // board and ascending legal moves (hex.py:151-159), zero padded
+    int base = 0;
+    for (int t0 = 0; t0 < nn; t0 += 32) {
+        const int t = t0 + lane;
+        const int c = t < nn ? cells[t] : 1;
+        if (t < nn) board[(size_t)i * nn + t] = c;
+        const uint32_t emp = __ballot_sync(AZ_FULL, c == 0);
+        if (c == 0) moves[(size_t)i * nn + base + __popc(emp & ((1u << lane) - 1u))] = t + 1;
+        base += __popc(emp);
+    }
+    for (int j = base + lane; j < nn; j += 32) moves[(size_t)i * nn + j] = 0;
+    if (lane == 0) {
+        reward[i] = h.reward;
+        color[i] = h.color;
+        result[i] = 0;          // states are recorded before the move: ongoing
+        num_moves[i] = k;
+    }
+}
+
 // =================================================================== C ABI
 
 static size_t az_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -842,6 +907,24 @@ int az_noise_sample(az_engine *e, float alpha, int k, int sim, float *out_dev, v
 {
     if (!e || !out_dev || k < 1 || k > e->nn || alpha <= 0.0f) return AZ_E_INVALID;
     AZ_LAUNCH(k_noise_sample, e, stream, alpha, k, sim, out_dev);
+}
+
+int az_replay_collate(const uint8_t *rows_dev, int row_bytes, const int64_t *index_dev, int count,
+                      int board_size, int32_t *board_dev, int32_t *moves_dev, float *probs_dev,
+                      float *reward_dev, int64_t *color_dev, int64_t *result_dev,
+                      int32_t *num_moves_dev, void *stream)
+{
+    if (!rows_dev || !index_dev || !board_dev || !moves_dev || !probs_dev || !reward_dev ||
+        !color_dev || !result_dev || !num_moves_dev || board_size < 2 || board_size > 19 || count < 0)
+        return AZ_E_INVALID;
+    const int nn = board_size * board_size, cs = (nn + 15) & ~15;
+    if (row_bytes < (int)sizeof(az_row_header) + cs + 4 * nn) return AZ_E_INVALID;
+    if (count == 0) return AZ_OK;
+    k_replay_collate<<<(count + AZ_WARPS_PER_CTA - 1) / AZ_WARPS_PER_CTA, AZ_WARPS_PER_CTA * 32, 0,
+                       (cudaStream_t)stream>>>(rows_dev, row_bytes, index_dev, count, board_size, cs,
+                                               board_dev, moves_dev, probs_dev, reward_dev, color_dev,
+                                               result_dev, num_moves_dev);
+    return az_check(cudaGetLastError());
 }
 
 int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t num_boards,

@@ -59,5 +59,24 @@ class Player:
         metrics['game_error'] = failed
         return examples, metrics
 
+    def read_device(self, size: int):
+        """Like ``read`` but the rows stay on the device (uint8
+        [R, row_bytes] tensor) for ``DeviceReplayBuffer.put``."""
+        import torch
+        eng = self.sp.eng
+        chunks, total = [], 0
+        metrics: Metrics = defaultdict(int)
+        games0 = self.sp.counters()['games']
+        while total < size:
+            self.sp.step_move()
+            count = min(eng.replay_count(), eng.replay.shape[0])
+            if count:
+                chunks.append(eng.replay[:count].clone())
+                eng.replay_clear()
+                total += count
+        metrics['games'] = self.sp.counters()['games'] - games0
+        metrics['moves_per_game'] = float(total)
+        return torch.cat(chunks), metrics
+
     def stop(self) -> None:
         self.running = False

@@ -211,6 +211,21 @@ int az_status(az_engine *e, int32_t *status_dev, void *stream);
  * AZ_BUF_PRIOR (AZ_PRIOR_PROBS layout) for the current leaves. */
 int az_stub_eval(az_engine *e, int mode, void *stream);
 
+/* ------------------------------------------------------- trainer feed */
+
+/* prep.torch_batch_replays (prep.py:24-39) on device-resident replay rows:
+ * for each of `count` row indices writes board int32[count][n*n], legal_moves
+ * int32[count][n*n] (ascending, 0-padded), moves_prob f32[count][n*n]
+ * (= as_distribution(visits, temperature), search_tree.py:327-344), reward
+ * f32, colour int64 (0/1), result int64 (0: recorded before the move),
+ * num_moves int32 (so the caller can trim the padding to the batch maximum
+ * like prep.pad, prep.py:70-86). */
+int az_replay_collate(const uint8_t *rows_dev, int row_bytes,
+                      const int64_t *index_dev, int count, int board_size,
+                      int32_t *board_dev, int32_t *moves_dev, float *probs_dev,
+                      float *reward_dev, int64_t *color_dev, int64_t *result_dev,
+                      int32_t *num_moves_dev, void *stream);
+
 /* ------------------------------------------------------- evaluator glue */
 
 /* HexNetwork input stage (network.py:138-142 + :71): Embedding(3,4) ->

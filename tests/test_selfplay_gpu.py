@@ -279,3 +279,71 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
     got_lp = torch.log_softmax(logits, 1)
     assert (got_lp - want_lp).abs().max() < 0.25
     assert (got_lp - want_lp).abs().mean() < 0.02
+
+
+def test_device_replay_buffer_collate_matches_host_format():
+    """DeviceReplayBuffer.sample == prep.torch_batch_replays over the same
+    rows (prep.py:24-39,70-86): boards, ascending zero-padded legal moves,
+    pi = as_distribution(visits, T) as float32 (1e-6), rewards; FIFO
+    wraparound and the fresh-counter accounting of replay_buffer.py:121-149;
+    a training step of the reference loss runs on the sampled batch."""
+    import azalea_b200 as az
+    from azalea_b200.selfplay import rows_to_dataframe
+    n = 5
+    _, rows = run_selfplay(G=64, n=n, sims=40, batch=4, moves=30)
+    buf = az.DeviceReplayBuffer(len(rows) + 7, n)
+    buf.put(torch.from_numpy(rows).cuda())
+    assert len(buf) == len(rows) and buf.fresh_counter == len(rows)
+    idx = torch.arange(len(rows))
+    batch = buf.collate(idx)
+    df = rows_to_dataframe(rows, n)
+    K = max(len(s.legal_moves) for s in df.state)
+    assert batch['legal_moves'].shape == (len(rows), K)
+    assert batch['board'].dtype == torch.int32 and batch['color'].dtype == torch.int64
+    lm = batch['legal_moves'].cpu().numpy()
+    mp = batch['moves_prob'].cpu().numpy()
+    bd = batch['board'].cpu().numpy()
+    for i in range(len(rows)):
+        k = len(df.state[i].legal_moves)
+        assert (bd[i] == df.state[i].board).all()
+        assert (lm[i, :k] == df.state[i].legal_moves).all() and (lm[i, k:] == 0).all()
+        assert np.abs(mp[i, :k] - df.moves_prob[i]).max() < 1e-6
+        assert (mp[i, k:] == 0).all()
+    assert (batch['reward'].cpu().numpy() == np.array(df.reward)).all()
+    assert (batch['color'].cpu().numpy() == [s.color for s in df.state]).all()
+    assert (batch['result'].cpu().numpy() == 0).all()
+    # wraparound keeps the newest rows (replay_buffer.py:134-149)
+    buf.put(torch.from_numpy(rows[:10]).cuda())
+    assert buf.write_idx == 3 and len(buf) == len(rows) + 7
+    assert (buf.rows[:3].cpu().numpy() == rows[7:10]).all()
+    # the reference's supervised step consumes the sampled batch
+    torch.manual_seed(0)
+    net = az.network.HexNetwork(n, 1, 16).cuda().train()
+    out, loss = net.run(buf.sample(32), compute_loss=True)
+    loss.backward()
+    assert torch.isfinite(loss) and out['value'].shape == (32,)
+
+
+def test_player_read_device_feeds_replay_buffer():
+    import azalea_b200 as az
+    p = az.Policy()
+    torch.manual_seed(0)
+    p.initialize(dict(device='cuda', network='HexNetwork', board_size=5,
+                      num_blocks=1, base_chans=32, simulations=30,
+                      search_batch_size=5, exploration_coef=0.5,
+                      exploration_depth=4, exploration_noise_alpha=0.03,
+                      exploration_noise_scale=0.25,
+                      exploration_temperature=1.0, seed=7))
+    agent = az.AzaleaAgent(lambda: az.HexGame(5), policy=p)
+    agent.settings['move_sampling'] = True
+    agent.settings['move_exploration'] = True
+    player = az.Player(None, [agent], num_games=64)
+    buf = az.DeviceReplayBuffer(500, 5)
+    buf.consume(0, player)
+    assert len(buf) == 0
+    metrics = buf.consume(128, player)
+    assert len(buf) >= 128 and metrics['games'] > 0
+    assert buf.fresh_counter >= 0
+    batch = buf.sample(64, trim=False)
+    assert batch['legal_moves'].shape == (64, 25)
+    assert torch.allclose(batch['moves_prob'].sum(1), torch.ones(64, device='cuda'), atol=1e-5)

@@ -50,14 +50,18 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-games', type=int, default=0)
     ap.add_argument('--skip-tree-only', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--sims', type=int, default=800, help='simulations per move')
+    ap.add_argument('--nodes-per-game', type=int, default=0)
+    args = ap.parse_args()
+    SEARCH['simulations'] = args.sims
+    return args
 
 
 def workload_name(args):
     ev = '6x64 resnet random-init bf16' if args.evaluator == 'net' \
         else f'stub evaluator mode {args.stub_mode}'
     return (f'Hex {args.board}x{args.board} lockstep self-play, {args.games} '
-            f'concurrent games/GPU, {ev}, 800 sims batch 10')
+            f'concurrent games/GPU, {ev}, {args.sims} sims batch 10')
 
 
 # ------------------------------------------------------------------ clocks --
@@ -205,8 +209,8 @@ def run_reference(args):
     oracle port (kind = 'port'), on all host cores."""
     cores = os.cpu_count() or 1
     threads = max(1, cores)
-    games = args.cpu_games or (min(64, max(8, threads)) if args.evaluator == 'net'
-                               else max(8, 2 * threads))
+    games = args.cpu_games or (4 * threads if args.evaluator == 'net'
+                               else 16 * threads)
     tot_sims = tot_plies = 0
     tot_secs = 0.0
     sample = ''
@@ -291,7 +295,8 @@ def run_ours(args):
     sp = LockstepSelfPlay(evaluator, num_games=args.games, board_size=args.board,
                           seed=0xBAD5EED5, rank=rank, world_size=world,
                           device=dev, cuda_graph=not args.no_graph,
-                          collect_replay=True, **SEARCH)
+                          collect_replay=True,
+                          nodes_per_game=args.nodes_per_game or None, **SEARCH)
     G, per_move = args.games, sp.sims_per_move
 
     # ---- warm-up (also captures the CUDA graph) ----
@@ -387,10 +392,17 @@ def run_ours(args):
     launches = sp.num_batches
     sel_avg_ms = sel_ms / launches
     achieved = sel_bytes / launches / (sel_avg_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+        key = f'{args.board}x{args.board}/{G}/' + ('noise' if sp.noise_scale else 'nonoise')
+        traffic = tj['k_select'][key]['traffic_bytes']
+    except Exception:
+        pass
     roofline = {
         'kernel': 'k_select', 'bound': 'hbm', 'achieved': achieved,
         'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-        'traffic': None, 'peak_source': peak_src,
+        'traffic': traffic, 'peak_source': peak_src,
         'avg_launch_ms': sel_avg_ms,
         'alg_bytes_per_launch': sel_bytes / launches,
         'alg_bytes_per_sim': sel_bytes / max(1, dk['simulations']),
@@ -423,7 +435,8 @@ def run_ours(args):
         sp2 = LockstepSelfPlay(StubEvaluator(2), num_games=args.games,
                                board_size=args.board, seed=1, rank=rank,
                                world_size=world, device=dev, cuda_graph=True,
-                               collect_replay=True, **SEARCH)
+                               collect_replay=True,
+                               nodes_per_game=args.nodes_per_game or None, **SEARCH)
         for _ in range(3):
             sp2.step_move()
         barrier()
@@ -446,9 +459,10 @@ def run_ours(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        games = args.cpu_games or min(64, max(8, cores))
-        r = cpu_selfplay_sample(args.board, args.evaluator, args.stub_mode,
-                                games if args.evaluator == 'net' else max(8, cores),
+        # bounded sample, ~10-30 s of CPU work: one ply of 4 games per core with
+        # the network, 16 whole games per core with the stub evaluator
+        games = args.cpu_games or (4 * cores if args.evaluator == 'net' else 16 * cores)
+        r = cpu_selfplay_sample(args.board, args.evaluator, args.stub_mode, games,
                                 1, cores)
         cpu_baseline = {'value': r['sims'] / r['seconds'], 'unit': UNIT,
                         'cores': cores, 'kind': 'port', 'sample': r['sample'],

@@ -318,3 +318,34 @@ def test_dirichlet_noise_distribution(alpha, k):
     assert abs((draws < small).mean() - (ref < small).mean()) < 0.01
     # different simulations and different games draw different vectors
     assert len({draws[i].tobytes() for i in range(0, len(draws), 97)}) > 300
+
+
+def test_deep_search_19x19_vs_oracle():
+    """Config 5 shape: 19x19, thousands of simulations per move, a node pool
+    of millions per game -- still bit-exact against the oracle."""
+    from azalea_b200 import Engine
+    n, G, sims, batch, coef, mode = 19, 2, 4000, 10, 0.5, stubs.ROUGH
+    eng = Engine(G, n, max_batch=batch, nodes_per_game=3_500_000)
+    games = [oracle.Hex(n) for _ in range(G)]
+    trees = [oracle.Tree(max_nodes=8_000_000) for _ in range(G)]
+    for ply in range(3):
+        eng.select_root(); eng.stub_eval(mode); eng.expand_root()
+        for _ in range(sims // batch + 1):
+            eng.select(batch, coef); eng.stub_eval(mode); eng.expand_backup()
+        v, w, p, k, rnw, nodes = (x.cpu().numpy() for x in eng.root_stats())
+        assert (eng.status().cpu().numpy() == 0).all()
+        move_ids = np.zeros(G, dtype=np.int32)
+        moves = np.zeros(G, dtype=np.int32)
+        for gi in range(G):
+            trees[gi].sample_paths_stub(games[gi], sims, batch, coef, mode)
+            ov, ow, op = trees[gi].root_stats()
+            assert bits(v[gi, :len(ov)]) == bits(ov), (ply, gi)
+            assert bits(w[gi, :len(ov)]) == bits(ow), (ply, gi)
+            assert nodes[gi] == trees[gi].num_nodes
+            move_ids[gi] = int(np.argsort(-ov, kind='stable')[gi])
+            moves[gi] = games[gi].legal_moves()[move_ids[gi]]
+            trees[gi].move(int(move_ids[gi]))
+            games[gi].step(int(moves[gi]))
+        eng.tree_move(move_ids)
+        eng.hex_step(moves)
+    assert nodes.max() > 3_000_000

@@ -11,6 +11,7 @@
 
 #include "az_kernels.cuh"
 #include "az_nn_glue.cuh"
+#include "az_tower.cuh"
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -929,8 +930,9 @@ int az_replay_collate(const uint8_t *rows_dev, int row_bytes, const int64_t *ind
 
 int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t num_boards,
                const void *table_dev, const float *bias_dev, void *out_dev, int channels,
-               void *stream)
+               int padded_layout, void *stream)
 {
+    if (padded_layout && channels != 64) return AZ_E_UNSUPPORTED;
     if (!cells_dev || !table_dev || !bias_dev || !out_dev || board_size < 2 || board_size > 19 ||
         channels < 8 || channels > AZ_NN_MAXC || (channels & 7) || num_boards < 0 ||
         cell_stride < board_size * board_size)
@@ -945,13 +947,14 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_nn_stem<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
         cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
-        bias_dev, (uint16_t *)out_dev, channels);
+        bias_dev, (uint16_t *)out_dev, channels, padded_layout);
     return az_check(cudaGetLastError());
 }
 
 int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const float *b_dev,
-                void *out_dev, int channels, int heads, void *stream)
+                void *out_dev, int channels, int heads, int padded_board_size, void *stream)
 {
+    if (padded_board_size && channels != 64) return AZ_E_UNSUPPORTED;
     if (!x_dev || !w_dev || !b_dev || !out_dev || channels < 8 || channels > AZ_NN_MAXC ||
         (channels & 7) || positions < 0)
         return AZ_E_INVALID;
@@ -962,7 +965,77 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
     long long blocks = (positions * (channels >> 3) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_nn_heads<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const uint16_t *)x_dev, (long long)positions, w_dev, b_dev, (uint16_t *)out_dev, channels);
+        (const uint16_t *)x_dev, (long long)positions, w_dev, b_dev, (uint16_t *)out_dev, channels,
+        padded_board_size);
+    return az_check(cudaGetLastError());
+}
+
+static int azt_halo(int n) { return (n + 2 + 7) & ~7; }
+
+static int azt_group_boards(int n)
+{
+    // two input stages of (halo + nb*rpb) rows + one layer's weights + 4 KB
+    // of static shared memory + the 1 KB the system reserves must fit in
+    // 227 KB.  Only a leading halo is staged: real outputs never read past
+    // their own board's pad row.
+    const int rpb = (n + 1) * (n + 1), halo = azt_halo(n);
+    const int max_rows = ((232448 - 6144 - AZT_WBYTES) / 2) / AZT_ROW - halo;
+    int nb = max_rows / rpb;
+    while (nb > 0 && (nb * rpb) % 8) nb--;
+    return nb;
+}
+
+int az_nn_tower_group(int board_size)
+{
+    if (board_size < 2 || board_size > 19) return AZ_E_INVALID;
+    const int nb = azt_group_boards(board_size);
+    return nb > 0 ? nb : AZ_E_UNSUPPORTED;
+}
+
+int az_nn_tower_halo(int board_size)
+{
+    if (board_size < 2 || board_size > 19) return AZ_E_INVALID;
+    return azt_halo(board_size);
+}
+
+int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, const void *resid_dev,
+                  void *out_dev, int board_size, int64_t num_boards, void *stream)
+{
+    if (!x_dev || !w_dev || !bias_dev || !out_dev || board_size < 2 || board_size > 19 || num_boards < 0)
+        return AZ_E_INVALID;
+    const int nb = azt_group_boards(board_size);
+    if (nb <= 0 || nb * (board_size + 1) * (board_size + 1) > 1024) return AZ_E_UNSUPPORTED;
+    if (num_boards % nb) return AZ_E_INVALID;
+    if (num_boards == 0) return AZ_OK;
+    azt_params p;
+    p.x = (const uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
+    p.resid = (const uint8_t *)resid_dev; p.out = (uint8_t *)out_dev;
+    p.n = board_size; p.halo = azt_halo(board_size); p.rpb = (board_size + 1) * (board_size + 1);
+    p.rows_group = nb * p.rpb; p.tiles = (p.rows_group + AZT_TSTRIDE - 1) / AZT_TSTRIDE;
+    p.stage_rows = p.halo + p.rows_group; p.groups = num_boards / nb;
+    { const char *dbg = getenv("AZT_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    const size_t smem = 2 * (size_t)p.stage_rows * AZT_ROW + AZT_WBYTES;
+    static int sm_count = 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncAttributes fa;
+        int rc = az_check(cudaFuncGetAttributes(&fa, k_conv3x3<true>));
+        if (rc != AZ_OK) return rc;
+        const int max_dyn = 232448 - (int)fa.sharedSizeBytes;      // 227 KB per block, static included
+        rc = az_check(cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        if (rc == AZ_OK)
+            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        if (rc != AZ_OK) return rc;
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)(p.groups < sm_count ? p.groups : sm_count);
+    if (resid_dev)
+        k_conv3x3<true><<<grid, 576, smem, (cudaStream_t)stream>>>(p);
+    else
+        k_conv3x3<false><<<grid, 576, smem, (cudaStream_t)stream>>>(p);
     return az_check(cudaGetLastError());
 }
 

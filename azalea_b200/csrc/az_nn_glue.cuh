@@ -45,12 +45,14 @@ __device__ __forceinline__ uint32_t az_pack_bf16x2(float lo, float hi)
 __global__ void __launch_bounds__(256)
 k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
           const uint16_t *__restrict__ table, const float *__restrict__ bias,
-          uint16_t *__restrict__ out, int C)
+          uint16_t *__restrict__ out, int C, int padded)
 {
+    // padded != 0: write the tower's layout (az_tower.cuh): row HALO + b*(n+1)^2
+    // + r*(n+1) + c, 16-byte chunk j at chunk j ^ (row & 7); C must be 64
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *stab = reinterpret_cast<uint16_t *>(smem_raw);                 // 36*C bf16
     uint16_t *spos = reinterpret_cast<uint16_t *>(smem_raw + 36 * C * 2);     // nn offsets (padded to even)
-    const int nn = n * n, pn = n + 2, pnn = pn * pn;
+    const int nn = n * n, pn = n + 2, pnn = pn * pn, pn1 = n + 1;
     int8_t *scell = reinterpret_cast<int8_t *>(smem_raw + 36 * C * 2 + ((nn + 1) & ~1) * 2);
     const int groups = C >> 3;
     const int cg = threadIdx.x % groups, tp = threadIdx.x / groups, ppt = blockDim.x / groups;
@@ -77,6 +79,7 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
         for (int q = 0; q < AZ_NN_STEM_BOARDS; q++) {
             if (b0 + q >= N) break;
             uint16_t *orow = out + (b0 + q) * (long long)nn * C + cg * 8;
+            const long long prow0 = ((n + 9) & ~7) + (b0 + q) * (long long)pn1 * pn1;   // halo = roundup(n + 2, 8)
             for (int p = tp; p < nn; p += ppt) {
                 const int8_t *sc = scell + q * pnn + spos[p];
                 float acc[8];
@@ -96,7 +99,13 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
                 o.y = az_pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
                 o.z = az_pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
                 o.w = az_pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-                *reinterpret_cast<uint4 *>(orow + (long long)p * C) = o;
+                if (padded) {
+                    // spos[p] = r * (n+2) + c  ->  r * (n+1) + c
+                    const long long R = prow0 + spos[p] - spos[p] / pn;
+                    *reinterpret_cast<uint4 *>(out + R * 64 + ((cg ^ (int)(R & 7)) << 3)) = o;
+                } else {
+                    *reinterpret_cast<uint4 *>(orow + (long long)p * C) = o;
+                }
             }
         }
     }
@@ -110,8 +119,10 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
 template <int H>
 __global__ void __launch_bounds__(256)
 k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict__ w,
-           const float *__restrict__ b, uint16_t *__restrict__ out, int C)
+           const float *__restrict__ b, uint16_t *__restrict__ out, int C, int padded_n)
 {
+    // padded_n != 0: x is in the tower's padded pre-swizzled layout for board
+    // size padded_n (C == 64); positions are still counted over real tiles
     const int groups = C >> 3;
     const int lane = threadIdx.x & 31, cg = lane % groups, sub = lane / groups;
     const int ppw = 32 / groups;                        // positions per warp per step
@@ -130,7 +141,15 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const long long p = p0 + u * ppw + sub;
-            v[u] = p < P ? *reinterpret_cast<const uint4 *>(x + p * C + cg * 8) : make_uint4(0, 0, 0, 0);
+            if (p < P && padded_n) {
+                const int nn = padded_n * padded_n, pn1 = padded_n + 1;
+                const long long bd = p / nn;
+                const int q = (int)(p - bd * nn);
+                const long long R = ((padded_n + 9) & ~7) + bd * pn1 * pn1 + (q / padded_n) * pn1 + q % padded_n;
+                v[u] = *reinterpret_cast<const uint4 *>(x + R * 64 + ((cg ^ (int)(R & 7)) << 3));
+            } else {
+                v[u] = p < P ? *reinterpret_cast<const uint4 *>(x + p * C + cg * 8) : make_uint4(0, 0, 0, 0);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {

@@ -82,6 +82,10 @@ class HexNetwork(nn.Module):
         self.encoder = nn.Embedding(3, 4)
         self.move_fc = nn.Linear(policy_chans * nn2, nn2)
         self._fast = None
+        # 'cudnn': the tower is twelve fused cuDNN calls (default);
+        # 'tcgen05': our implicit-GEMM kernel (csrc/az_tower.cuh), 64 channels only
+        import os
+        self.tower = os.environ.get('AZALEA_B200_TOWER', 'cudnn')
         nnet = sum(p.nelement() for p in self.parameters())
         nenc = sum(p.nelement() for p in self.encoder.parameters())
         logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)
@@ -172,6 +176,22 @@ class HexNetwork(nn.Module):
         fast['blocks'] = [(pack(*_fold(b.conv1, b.bn1)),
                            pack(*_fold(b.conv2, b.bn2)))
                           for b in self.resblocks]
+        # the same layers packed for az_nn_conv3x3 (csrc/az_tower.cuh):
+        # [tap = ky*3+kx][c_out][c_in] bf16, 16-byte chunk j of row r stored
+        # at chunk j ^ (r & 7); bias stays fp32
+        fast['tower'] = None
+        if ws.shape[0] == 64 and dtype == torch.bfloat16:
+            def pack_tower(conv, bn):
+                w, b = _fold(conv, bn)
+                t = w.permute(2, 3, 0, 1).reshape(9 * 64, 8, 8)
+                rows = torch.arange(9 * 64, device=t.device)
+                idx = (torch.arange(8, device=t.device)[None, :] ^ (rows[:, None] & 7))
+                sw = torch.empty_like(t)
+                sw.scatter_(1, idx[:, :, None].expand(-1, -1, 8), t)
+                return keep(sw.reshape(9 * 64, 64)), keep32(b)
+            fast['tower'] = [(pack_tower(b.conv1, b.bn1), pack_tower(b.conv2, b.bn2))
+                             for b in self.resblocks]
+        fast['tower_buf'] = old['tower_buf'] if old is not None else {}
         # the two 1x1 head convolutions read the same activations: one conv;
         # the two first fully connected layers read its output: one GEMM over
         # the channels-last flattening (hw-major, channel-minor), so no
@@ -212,6 +232,8 @@ class HexNetwork(nn.Module):
         glue = (cells.is_cuda and f['dtype'] == torch.bfloat16
                 and C_ in (32, 64, 128) and cells.dtype == torch.int8
                 and cells.stride(1) == 1)
+        if glue and self.tower == 'tcgen05' and f['tower'] is not None:
+            return self._evaluate_cells_tcgen05(cells)
         if glue:
             # our kernels at both ends of the tower (csrc/az_nn_glue.cuh)
             from . import _cabi
@@ -223,7 +245,7 @@ class HexNetwork(nn.Module):
                 ctypes.c_void_p(cells.data_ptr()), cells.stride(0), n, N,
                 ctypes.c_void_p(f['stem_table'].data_ptr()),
                 ctypes.c_void_p(f['stem_bias'].data_ptr()),
-                ctypes.c_void_p(x.data_ptr()), C_, stream))
+                ctypes.c_void_p(x.data_ptr()), C_, 0, stream))
             x = x.permute(0, 3, 1, 2)       # NCHW view of NHWC memory
         else:
             idx = cells[:, :n * n].to(torch.int32)
@@ -246,7 +268,7 @@ class HexNetwork(nn.Module):
                     ctypes.c_void_p(xh.data_ptr()), N * n * n,
                     ctypes.c_void_p(f['heads_w32'].data_ptr()),
                     ctypes.c_void_p(f['heads_b32'].data_ptr()),
-                    ctypes.c_void_p(flat.data_ptr()), C_, 6, stream))
+                    ctypes.c_void_p(flat.data_ptr()), C_, 6, 0, stream))
                 h = None
             else:
                 h = torch.cudnn_convolution_relu(x, *f['heads'], one, nopad, one, 1)
@@ -265,3 +287,39 @@ class HexNetwork(nn.Module):
         value = torch.tanh(F.linear(F.relu(y[:, :k2]), *f['value_fc3'])).squeeze(1)
         logits = y[:, k2:]
         return value.float(), logits.float()
+
+    @torch.no_grad()
+    def _evaluate_cells_tcgen05(self, cells):
+        """evaluate_cells with the whole tower on our tcgen05 convolution
+        (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the padded
+        pre-swizzled activation layout (residual added in the epilogue, in
+        place) -> heads kernel -> one GEMM."""
+        import ctypes
+        from . import _cabi
+        f = self._fast
+        L = _cabi.lib()
+        n, N, dev = self.board_size, cells.shape[0], cells.device
+        nb, halo = L.az_nn_tower_group(n), L.az_nn_tower_halo(n)
+        npad = (N + nb - 1) // nb * nb
+        rows = halo + npad * (n + 1) ** 2 + halo
+        bufs = f['tower_buf'].get((npad, dev))
+        if bufs is None:
+            # halos and pad cells must be zero; the kernels keep them zero
+            bufs = (torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
+                    torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev))
+            f['tower_buf'][(npad, dev)] = bufs
+        x, y = bufs
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
+                                 p(f['stem_bias']), p(x), 64, 1, stream))
+        for (w1, b1), (w2, b2) in f['tower']:
+            _cabi.check(L.az_nn_conv3x3(p(x), p(w1), p(b1), None, p(y), n, npad, stream))
+            _cabi.check(L.az_nn_conv3x3(p(y), p(w2), p(b2), p(x), p(x), n, npad, stream))
+        flat = torch.empty(N, n * n * 6, dtype=torch.bfloat16, device=dev)
+        _cabi.check(L.az_nn_heads(p(x), N * n * n, p(f['heads_w32']), p(f['heads_b32']),
+                                  p(flat), 64, 6, n, stream))
+        yfc = F.linear(flat, *f['fc'])
+        k2 = f['nfc2']
+        value = torch.tanh(F.linear(F.relu(yfc[:, :k2]), *f['value_fc3'])).squeeze(1)
+        return value.float(), yfc[:, k2:].float()

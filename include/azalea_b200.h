@@ -236,13 +236,30 @@ int az_replay_collate(const uint8_t *rows_dev, int row_bytes,
  * f32 [channels]; out bf16 [num_boards][n*n][channels] (NHWC). */
 int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size,
                int64_t num_boards, const void *table_dev, const float *bias_dev,
-               void *out_dev, int channels, void *stream);
+               void *out_dev, int channels, int padded_layout, void *stream);
 /* Both 1x1 head convolutions + BN + ReLU (network.py:75-76,82-83) in one
  * pass: x bf16 [positions][channels] (NHWC), w f32 [heads][channels], b f32
  * [heads] -> out bf16 [positions][heads]; heads = 6 (2 value + 4 policy). */
 int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev,
                 const float *b_dev, void *out_dev, int channels, int heads,
-                void *stream);
+                int padded_board_size, void *stream);
+
+/* One tower convolution (Resblock.conv1/conv2 + BatchNorm + ReLU, with the
+ * residual add for conv2; network.py:17-39) as a tcgen05 implicit GEMM, 64 ->
+ * 64 channels (csrc/az_tower.cuh).  Activations use the tower's padded,
+ * pre-swizzled layout: bf16 rows of 64 channels, row = halo + board*(n+1)^2 +
+ * r*(n+1) + c with halo = az_nn_tower_halo(n), pad cells (r == n or c == n)
+ * zero, 16-byte chunk j of row R stored at chunk j ^ (R & 7); a buffer holds
+ * halo + boards*(n+1)^2 + halo rows and its halos must be zero.  padded_layout = 1 makes
+ * az_nn_stem write it, padded_board_size = n makes az_nn_heads read it.
+ * w: bf16 [9 taps][64 c_out][64 c_in] with the same chunk swizzle (by c_out),
+ * bias f32 [64], resid (nullable) in the activation layout.  num_boards must
+ * be a multiple of az_nn_tower_group(board_size). */
+int az_nn_tower_group(int board_size);
+int az_nn_tower_halo(int board_size);     /* halo rows: roundup(n + 2, 8) */
+int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev,
+                  const void *resid_dev, void *out_dev, int board_size,
+                  int64_t num_boards, void *stream);
 
 /* Test aid for the root exploration noise (mcts.py:126-131), which only has
  * statistical parity with RandomState.dirichlet: writes the Dirichlet(alpha)

@@ -252,7 +252,7 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
     _cabi.check(L.az_nn_stem(ctypes.c_void_p(cells.data_ptr()), cs, n, N,
                              ctypes.c_void_p(f['stem_table'].data_ptr()),
                              ctypes.c_void_p(f['stem_bias'].data_ptr()),
-                             ctypes.c_void_p(out.data_ptr()), chans, stream))
+                             ctypes.c_void_p(out.data_ptr()), chans, 0, stream))
     with torch.no_grad():
         x = net.encoder(cells[:, :nn].long().view(N, n, n)).permute(0, 3, 1, 2)
         want = F.relu(net.bn1(net.conv1(x))).permute(0, 2, 3, 1)
@@ -265,7 +265,7 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
     _cabi.check(L.az_nn_heads(ctypes.c_void_p(xin.data_ptr()), N * nn,
                               ctypes.c_void_p(f['heads_w32'].data_ptr()),
                               ctypes.c_void_p(f['heads_b32'].data_ptr()),
-                              ctypes.c_void_p(hout.data_ptr()), chans, 6, stream))
+                              ctypes.c_void_p(hout.data_ptr()), chans, 6, 0, stream))
     want = F.relu(xin.float() @ f['heads_w32'].t() + f['heads_b32'])
     got = hout.float()
     assert ((got - want).abs() <= want.abs() * 2 ** -7 + 1e-3).all()
@@ -347,3 +347,80 @@ def test_player_read_device_feeds_replay_buffer():
     batch = buf.sample(64, trim=False)
     assert batch['legal_moves'].shape == (64, 25)
     assert torch.allclose(batch['moves_prob'].sum(1), torch.ones(64, device='cuda'), atol=1e-5)
+
+
+@pytest.mark.parametrize('n,N', ((11, 64), (11, 1028), (19, 9), (7, 90)))
+def test_tcgen05_conv3x3_matches_torch(n, N):
+    """az_nn_conv3x3 (csrc/az_tower.cuh: tcgen05 implicit GEMM over the
+    padded pre-swizzled layout, N = 192 tap stacking) against F.conv2d in
+    fp32 on the same bf16 inputs: bias, ReLU, residual; pad cells stay zero.
+    Tolerance = one bf16 rounding of the output (2^-8 relative + 1e-2)."""
+    import ctypes
+    import torch.nn.functional as F
+    from azalea_b200 import _cabi
+    L = _cabi.lib()
+    nb, halo = L.az_nn_tower_group(n), L.az_nn_tower_halo(n)
+    N = (N + nb - 1) // nb * nb
+    rpb = (n + 1) ** 2
+
+    def swz(t):
+        R = t.shape[0]
+        idx = torch.arange(8, device=t.device)[None, :] ^ (torch.arange(R, device=t.device)[:, None] & 7)
+        out = torch.empty_like(t.view(R, 8, 8))
+        out.scatter_(1, idx[:, :, None].expand(R, 8, 8), t.view(R, 8, 8))
+        return out.view(R, 64)
+
+    def unswz(t):
+        R = t.shape[0]
+        idx = torch.arange(8, device=t.device)[None, :] ^ (torch.arange(R, device=t.device)[:, None] & 7)
+        return torch.gather(t.view(R, 8, 8), 1, idx[:, :, None].expand(R, 8, 8)).reshape(R, 64)
+
+    def to_padded(x):
+        pd = torch.zeros(N, n + 1, n + 1, 64, dtype=x.dtype, device=x.device)
+        pd[:, :n, :n] = x
+        buf = torch.zeros(halo + N * rpb + halo, 64, dtype=x.dtype, device=x.device)
+        buf[halo:halo + N * rpb] = pd.view(-1, 64)
+        return swz(buf)
+
+    torch.manual_seed(n)
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    r = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    w = (torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16)
+    b = torch.randn(64, device='cuda') * 0.1
+    xp, rp = to_padded(x), to_padded(r)
+    wp = swz(w.permute(2, 3, 0, 1).reshape(9 * 64, 64).contiguous())
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    for use_res in (False, True):
+        out = torch.full_like(xp, 3.0)
+        out[:halo] = 0
+        out[-halo:] = 0
+        _cabi.check(L.az_nn_conv3x3(p(xp), p(wp), p(b), p(rp) if use_res else None, p(out), n, N, stream))
+        got = unswz(out)[halo:halo + N * rpb].view(N, n + 1, n + 1, 64).float()
+        want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, padding=1)
+        if use_res:
+            want = want + r.permute(0, 3, 1, 2).float()
+        want = F.relu(want).permute(0, 2, 3, 1)
+        assert ((got[:, :n, :n] - want).abs() <= want.abs() * 2 ** -8 + 1e-2).all()
+        assert float(got[:, n].abs().max()) == 0 and float(got[:, :, n].abs().max()) == 0
+
+
+def test_tcgen05_tower_matches_cudnn_tower():
+    """The whole evaluator with the tcgen05 tower (AZALEA_B200_TOWER=tcgen05)
+    against the default cuDNN tower on the same weights: both are bf16 with
+    fp32 accumulation, so values agree to ~1e-2 and log-priors to ~0.1."""
+    from azalea_b200.network import HexNetwork
+    torch.manual_seed(3)
+    net = HexNetwork(11, 6, 64).eval().cuda()
+    net.prepare_inference(torch.bfloat16)
+    cells = torch.zeros(1001, 128, dtype=torch.int8, device='cuda')
+    cells[:, :121] = torch.randint(0, 3, (1001, 121), device='cuda', dtype=torch.int8)
+    net.tower = 'cudnn'
+    v0, l0 = net.evaluate_cells(cells)
+    net.tower = 'tcgen05'
+    v1, l1 = net.evaluate_cells(cells)
+    v2, l2 = net.evaluate_cells(cells)          # buffers are reused: same answer again
+    assert torch.equal(v1, v2) and torch.equal(l1, l2)
+    assert (v0 - v1).abs().max() < 0.03
+    lp0, lp1 = torch.log_softmax(l0, 1), torch.log_softmax(l1, 1)
+    assert (lp0 - lp1).abs().max() < 0.15 and (lp0 - lp1).abs().mean() < 0.01

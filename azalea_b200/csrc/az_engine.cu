@@ -972,24 +972,10 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
 
 static int azt_halo(int n) { return (n + 2 + 7) & ~7; }
 
-static int azt_group_boards(int n)
-{
-    // two input stages of (halo + nb*rpb) rows + one layer's weights + 4 KB
-    // of static shared memory + the 1 KB the system reserves must fit in
-    // 227 KB.  Only a leading halo is staged: real outputs never read past
-    // their own board's pad row.
-    const int rpb = (n + 1) * (n + 1), halo = azt_halo(n);
-    const int max_rows = ((232448 - 6144 - AZT_WBYTES) / 2) / AZT_ROW - halo;
-    int nb = max_rows / rpb;
-    while (nb > 0 && (nb * rpb) % 8) nb--;
-    return nb;
-}
-
 int az_nn_tower_group(int board_size)
 {
-    if (board_size < 2 || board_size > 19) return AZ_E_INVALID;
-    const int nb = azt_group_boards(board_size);
-    return nb > 0 ? nb : AZ_E_UNSUPPORTED;
+    /* any number of boards is accepted (kept for ABI stability) */
+    return (board_size < 2 || board_size > 19) ? AZ_E_INVALID : 1;
 }
 
 int az_nn_tower_halo(int board_size)
@@ -998,44 +984,44 @@ int az_nn_tower_halo(int board_size)
     return azt_halo(board_size);
 }
 
+int64_t az_nn_tower_rows(int board_size, int64_t num_boards)
+{
+    if (board_size < 2 || board_size > 19 || num_boards < 0) return AZ_E_INVALID;
+    /* halo + data rows + spare rows so that the last tile's input chunk
+     * (AZT_CHUNK_ROWS rows from an 8-aligned start) stays inside the buffer */
+    return azt_halo(board_size) + num_boards * (board_size + 1) * (board_size + 1) + AZT_CHUNK_ROWS + 8;
+}
+
 int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, const void *resid_dev,
                   void *out_dev, int board_size, int64_t num_boards, void *stream)
 {
     if (!x_dev || !w_dev || !bias_dev || !out_dev || board_size < 2 || board_size > 19 || num_boards < 0)
         return AZ_E_INVALID;
-    const int nb = azt_group_boards(board_size);
-    if (nb <= 0 || nb * (board_size + 1) * (board_size + 1) > 1024) return AZ_E_UNSUPPORTED;
-    if (num_boards % nb) return AZ_E_INVALID;
     if (num_boards == 0) return AZ_OK;
     azt_params p;
     p.x = (const uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.resid = (const uint8_t *)resid_dev; p.out = (uint8_t *)out_dev;
     p.n = board_size; p.halo = azt_halo(board_size); p.rpb = (board_size + 1) * (board_size + 1);
-    p.rows_group = nb * p.rpb; p.tiles = (p.rows_group + AZT_TSTRIDE - 1) / AZT_TSTRIDE;
-    p.stage_rows = p.halo + p.rows_group; p.groups = num_boards / nb;
+    p.rows = (long long)num_boards * p.rpb;
+    p.tiles = (p.rows + AZT_TSTRIDE - 1) / AZT_TSTRIDE;
     { const char *dbg = getenv("AZT_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
-    const size_t smem = 2 * (size_t)p.stage_rows * AZT_ROW + AZT_WBYTES;
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaFuncAttributes fa;
-        int rc = az_check(cudaFuncGetAttributes(&fa, k_conv3x3<true>));
-        if (rc != AZ_OK) return rc;
-        const int max_dyn = 232448 - (int)fa.sharedSizeBytes;      // 227 KB per block, static included
-        rc = az_check(cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+        int rc = az_check(cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc == AZ_OK)
-            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn));
+            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc != AZ_OK) return rc;
         attr_set = true;
     }
-    const unsigned grid = (unsigned)(p.groups < sm_count ? p.groups : sm_count);
+    const unsigned grid = (unsigned)(p.tiles < sm_count ? p.tiles : sm_count);
     if (resid_dev)
-        k_conv3x3<true><<<grid, 576, smem, (cudaStream_t)stream>>>(p);
+        k_conv3x3<true><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     else
-        k_conv3x3<false><<<grid, 576, smem, (cudaStream_t)stream>>>(p);
+        k_conv3x3<false><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return az_check(cudaGetLastError());
 }
 

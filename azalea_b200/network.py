@@ -299,9 +299,8 @@ class HexNetwork(nn.Module):
         f = self._fast
         L = _cabi.lib()
         n, N, dev = self.board_size, cells.shape[0], cells.device
-        nb, halo = L.az_nn_tower_group(n), L.az_nn_tower_halo(n)
-        npad = (N + nb - 1) // nb * nb
-        rows = halo + npad * (n + 1) ** 2 + halo
+        npad = N
+        rows = L.az_nn_tower_rows(n, N)
         bufs = f['tower_buf'].get((npad, dev))
         if bufs is None:
             # halos and pad cells must be zero; the kernels keep them zero

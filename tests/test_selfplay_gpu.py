@@ -349,7 +349,7 @@ def test_player_read_device_feeds_replay_buffer():
     assert torch.allclose(batch['moves_prob'].sum(1), torch.ones(64, device='cuda'), atol=1e-5)
 
 
-@pytest.mark.parametrize('n,N', ((11, 64), (11, 1028), (19, 9), (7, 90)))
+@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1)))
 def test_tcgen05_conv3x3_matches_torch(n, N):
     """az_nn_conv3x3 (csrc/az_tower.cuh: tcgen05 implicit GEMM over the
     padded pre-swizzled layout, N = 192 tap stacking) against F.conv2d in
@@ -359,8 +359,7 @@ def test_tcgen05_conv3x3_matches_torch(n, N):
     import torch.nn.functional as F
     from azalea_b200 import _cabi
     L = _cabi.lib()
-    nb, halo = L.az_nn_tower_group(n), L.az_nn_tower_halo(n)
-    N = (N + nb - 1) // nb * nb
+    halo = L.az_nn_tower_halo(n)
     rpb = (n + 1) ** 2
 
     def swz(t):
@@ -378,7 +377,7 @@ def test_tcgen05_conv3x3_matches_torch(n, N):
     def to_padded(x):
         pd = torch.zeros(N, n + 1, n + 1, 64, dtype=x.dtype, device=x.device)
         pd[:, :n, :n] = x
-        buf = torch.zeros(halo + N * rpb + halo, 64, dtype=x.dtype, device=x.device)
+        buf = torch.zeros(L.az_nn_tower_rows(n, N), 64, dtype=x.dtype, device=x.device)
         buf[halo:halo + N * rpb] = pd.view(-1, 64)
         return swz(buf)
 
@@ -394,7 +393,7 @@ def test_tcgen05_conv3x3_matches_torch(n, N):
     for use_res in (False, True):
         out = torch.full_like(xp, 3.0)
         out[:halo] = 0
-        out[-halo:] = 0
+        out[halo + N * rpb:] = 0
         _cabi.check(L.az_nn_conv3x3(p(xp), p(wp), p(b), p(rp) if use_res else None, p(out), n, N, stream))
         got = unswz(out)[halo:halo + N * rpb].view(N, n + 1, n + 1, 64).float()
         want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, padding=1)

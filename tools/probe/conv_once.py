@@ -4,7 +4,7 @@ from azalea_b200 import _cabi
 L = _cabi.lib()
 n, N = 11, 40960
 H = L.az_nn_tower_halo(n)
-rows = H + N * (n + 1) ** 2 + H
+rows = L.az_nn_tower_rows(n, N)
 x = (torch.randn(rows, 64, device='cuda') * 0.5).to(torch.bfloat16)
 r = (torch.randn(rows, 64, device='cuda') * 0.5).to(torch.bfloat16)
 w = (torch.randn(9 * 64, 64, device='cuda') * 0.05).to(torch.bfloat16)

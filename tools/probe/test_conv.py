@@ -23,7 +23,7 @@ def to_padded(x):           # x [N, n, n, 64] bf16
     HALO = L.az_nn_tower_halo(n)
     p = torch.zeros(N, n + 1, n + 1, 64, dtype=x.dtype, device=x.device)
     p[:, :n, :n] = x
-    buf = torch.zeros(HALO + N * (n + 1) ** 2 + HALO, 64, dtype=x.dtype, device=x.device)
+    buf = torch.zeros(L.az_nn_tower_rows(n, N), 64, dtype=x.dtype, device=x.device)
     buf[HALO:HALO + N * (n + 1) ** 2] = p.view(-1, 64)
     return swz_rows(buf)
 
@@ -50,7 +50,7 @@ for n, N in ((11, 8), (11, 4096), (19, 5), (11, 40960)):
     for use_res in (False, True):
         out = torch.full_like(xp, 7.0)
         H = L.az_nn_tower_halo(n)
-        out[:H] = 0; out[-H:] = 0
+        out[:H] = 0; out[H + N * (n + 1) ** 2:] = 0
         rc = L.az_nn_conv3x3(ctypes.c_void_p(xp.data_ptr()), ctypes.c_void_p(wp.data_ptr()),
                              ctypes.c_void_p(b.data_ptr()),
                              ctypes.c_void_p(rp.data_ptr()) if use_res else None,

@@ -970,26 +970,24 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
     return az_check(cudaGetLastError());
 }
 
-static int azt_halo(int n) { return (n + 2 + 7) & ~7; }
-
 int az_nn_tower_group(int board_size)
 {
-    /* any number of boards is accepted (kept for ABI stability) */
-    return (board_size < 2 || board_size > 19) ? AZ_E_INVALID : 1;
+    /* boards that share one 128-row slab */
+    return (board_size < 2 || board_size > 19) ? AZ_E_INVALID : 128 / (board_size + 1);
 }
 
 int az_nn_tower_halo(int board_size)
 {
-    if (board_size < 2 || board_size > 19) return AZ_E_INVALID;
-    return azt_halo(board_size);
+    return (board_size < 2 || board_size > 19) ? AZ_E_INVALID : AZT_HALO;
 }
 
 int64_t az_nn_tower_rows(int board_size, int64_t num_boards)
 {
     if (board_size < 2 || board_size > 19 || num_boards < 0) return AZ_E_INVALID;
-    /* halo + data rows + spare rows so that the last tile's input chunk
-     * (AZT_CHUNK_ROWS rows from an 8-aligned start) stays inside the buffer */
-    return azt_halo(board_size) + num_boards * (board_size + 1) * (board_size + 1) + AZT_CHUNK_ROWS + 8;
+    const int bpg = 128 / (board_size + 1);
+    const int64_t groups = (num_boards + bpg - 1) / bpg;
+    /* 8 zero rows, n slabs of 128 rows per group, 16 zero rows */
+    return AZT_HALO + groups * board_size * 128 + 16;
 }
 
 int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, const void *resid_dev,
@@ -1001,9 +999,8 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, c
     azt_params p;
     p.x = (const uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.resid = (const uint8_t *)resid_dev; p.out = (uint8_t *)out_dev;
-    p.n = board_size; p.halo = azt_halo(board_size); p.rpb = (board_size + 1) * (board_size + 1);
-    p.rows = (long long)num_boards * p.rpb;
-    p.tiles = (p.rows + AZT_TSTRIDE - 1) / AZT_TSTRIDE;
+    p.n = board_size; p.bpg = 128 / (board_size + 1);
+    p.groups = (num_boards + p.bpg - 1) / p.bpg;
     { const char *dbg = getenv("AZT_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
     static int sm_count = 0;
     static bool attr_set = false;
@@ -1017,7 +1014,7 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, c
         if (rc != AZ_OK) return rc;
         attr_set = true;
     }
-    const unsigned grid = (unsigned)(p.tiles < sm_count ? p.tiles : sm_count);
+    const unsigned grid = (unsigned)(p.groups < sm_count ? p.groups : sm_count);
     if (resid_dev)
         k_conv3x3<true><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     else

@@ -47,8 +47,9 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
           const uint16_t *__restrict__ table, const float *__restrict__ bias,
           uint16_t *__restrict__ out, int C, int padded)
 {
-    // padded != 0: write the tower's layout (az_tower.cuh): row HALO + b*(n+1)^2
-    // + r*(n+1) + c, 16-byte chunk j at chunk j ^ (row & 7); C must be 64
+    // padded != 0: write the tower's slab layout (az_tower.cuh): row 8 +
+    // 128 * ((b / bpg) * (n+1) + y) + (b % bpg) * (n+1) + x, bpg = 128 / (n+1),
+    // 16-byte chunk j at chunk j ^ (row & 7); C must be 64
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *stab = reinterpret_cast<uint16_t *>(smem_raw);                 // 36*C bf16
     uint16_t *spos = reinterpret_cast<uint16_t *>(smem_raw + 36 * C * 2);     // nn offsets (padded to even)
@@ -79,7 +80,8 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
         for (int q = 0; q < AZ_NN_STEM_BOARDS; q++) {
             if (b0 + q >= N) break;
             uint16_t *orow = out + (b0 + q) * (long long)nn * C + cg * 8;
-            const long long prow0 = ((n + 9) & ~7) + (b0 + q) * (long long)pn1 * pn1;   // halo = roundup(n + 2, 8)
+            const int bpg = 128 / pn1;
+            const long long prow0 = 8 + ((b0 + q) / bpg) * (long long)n * 128 + ((b0 + q) % bpg) * pn1;
             for (int p = tp; p < nn; p += ppt) {
                 const int8_t *sc = scell + q * pnn + spos[p];
                 float acc[8];
@@ -100,8 +102,8 @@ k_nn_stem(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
                 o.z = az_pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
                 o.w = az_pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
                 if (padded) {
-                    // spos[p] = r * (n+2) + c  ->  r * (n+1) + c
-                    const long long R = prow0 + spos[p] - spos[p] / pn;
+                    // spos[p] = y * (n+2) + x  ->  y * 128 + x
+                    const long long R = prow0 + (spos[p] / pn) * 128 + spos[p] % pn;
                     *reinterpret_cast<uint4 *>(out + R * 64 + ((cg ^ (int)(R & 7)) << 3)) = o;
                 } else {
                     *reinterpret_cast<uint4 *>(orow + (long long)p * C) = o;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256)
 k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict__ w,
            const float *__restrict__ b, uint16_t *__restrict__ out, int C, int padded_n)
 {
-    // padded_n != 0: x is in the tower's padded pre-swizzled layout for board
+    // padded_n != 0: x is in the tower's slab layout (az_tower.cuh) for board
     // size padded_n (C == 64); positions are still counted over real tiles
     const int groups = C >> 3;
     const int lane = threadIdx.x & 31, cg = lane % groups, sub = lane / groups;
@@ -145,7 +147,8 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
                 const int nn = padded_n * padded_n, pn1 = padded_n + 1;
                 const long long bd = p / nn;
                 const int q = (int)(p - bd * nn);
-                const long long R = ((padded_n + 9) & ~7) + bd * pn1 * pn1 + (q / padded_n) * pn1 + q % padded_n;
+                const int bpg = 128 / pn1;
+                const long long R = 8 + ((bd / bpg) * padded_n + q / padded_n) * 128 + (bd % bpg) * pn1 + q % padded_n;
                 v[u] = *reinterpret_cast<const uint4 *>(x + R * 64 + ((cg ^ (int)(R & 7)) << 3));
             } else {
                 v[u] = p < P ? *reinterpret_cast<const uint4 *>(x + p * C + cg * 8) : make_uint4(0, 0, 0, 0);

@@ -177,18 +177,15 @@ class HexNetwork(nn.Module):
                            pack(*_fold(b.conv2, b.bn2)))
                           for b in self.resblocks]
         # the same layers packed for az_nn_conv3x3 (csrc/az_tower.cuh):
-        # [tap = ky*3+kx][c_out][c_in] bf16, 16-byte chunk j of row r stored
-        # at chunk j ^ (r & 7); bias stays fp32
+        # [kx][ky][c_out][c_in] bf16, 16-byte chunk j of row r stored at
+        # chunk j ^ (r & 7); bias stays fp32
         fast['tower'] = None
         if ws.shape[0] == 64 and dtype == torch.bfloat16:
+            from .tower_layout import pack_conv_weights
+
             def pack_tower(conv, bn):
                 w, b = _fold(conv, bn)
-                t = w.permute(2, 3, 0, 1).reshape(9 * 64, 8, 8)
-                rows = torch.arange(9 * 64, device=t.device)
-                idx = (torch.arange(8, device=t.device)[None, :] ^ (rows[:, None] & 7))
-                sw = torch.empty_like(t)
-                sw.scatter_(1, idx[:, :, None].expand(-1, -1, 8), t)
-                return keep(sw.reshape(9 * 64, 64)), keep32(b)
+                return keep(pack_conv_weights(w.to(dev, dtype))), keep32(b)
             fast['tower'] = [(pack_tower(b.conv1, b.bn1), pack_tower(b.conv2, b.bn2))
                              for b in self.resblocks]
         fast['tower_buf'] = old['tower_buf'] if old is not None else {}
@@ -291,9 +288,9 @@ class HexNetwork(nn.Module):
     @torch.no_grad()
     def _evaluate_cells_tcgen05(self, cells):
         """evaluate_cells with the whole tower on our tcgen05 convolution
-        (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the padded
-        pre-swizzled activation layout (residual added in the epilogue, in
-        place) -> heads kernel -> one GEMM."""
+        (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the slab
+        activation layout (residual added in the epilogue, in place) -> heads
+        kernel -> one GEMM."""
         import ctypes
         from . import _cabi
         f = self._fast

@@ -246,18 +246,19 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev,
 
 /* One tower convolution (Resblock.conv1/conv2 + BatchNorm + ReLU, with the
  * residual add for conv2; network.py:17-39) as a tcgen05 implicit GEMM, 64 ->
- * 64 channels (csrc/az_tower.cuh).  Activations use the tower's padded,
- * pre-swizzled layout: bf16 rows of 64 channels, row = halo + board*(n+1)^2 +
- * r*(n+1) + c with halo = az_nn_tower_halo(n), pad cells (r == n or c == n)
- * zero, 16-byte chunk j of row R stored at chunk j ^ (R & 7); a buffer holds
- * az_nn_tower_rows(n, boards) rows; everything outside the data rows must be
- * zero (the kernels never write there).  padded_layout = 1 makes
- * az_nn_stem write it, padded_board_size = n makes az_nn_heads read it.
- * w: bf16 [9 taps][64 c_out][64 c_in] with the same chunk swizzle (by c_out),
- * bias f32 [64], resid (nullable) in the activation layout (out may alias
- * resid). */
+ * 64 channels (csrc/az_tower.cuh).  Activations use the tower's slab layout:
+ * bf16 rows of 64 channels; one 128-row slab holds board row y of bpg =
+ * az_nn_tower_group(n) = 128 / (n+1) boards:
+ *     row = 8 + 128 * ((board / bpg) * n + y) + (board % bpg) * (n+1) + x
+ * with one zero pad cell per board row (x == n), zero rows elsewhere, and
+ * 16-byte chunk j of row R stored at chunk j ^ (R & 7).  A buffer holds az_nn_tower_rows(n, boards) rows; everything
+ * that is not a real cell must be zero (the kernels keep it zero).
+ * padded_layout = 1 makes az_nn_stem write this layout, padded_board_size = n
+ * makes az_nn_heads read it.  w: bf16 [3 kx][3 ky][64 c_out][64 c_in] with the
+ * same chunk swizzle (by c_out), bias f32 [64], resid (nullable) in the
+ * activation layout (out may alias resid). */
 int az_nn_tower_group(int board_size);
-int az_nn_tower_halo(int board_size);     /* halo rows: roundup(n + 2, 8) */
+int az_nn_tower_halo(int board_size);     /* zero rows in front of the first slab (8) */
 int64_t az_nn_tower_rows(int board_size, int64_t num_boards);   /* rows a buffer must hold */
 int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev,
                   const void *resid_dev, void *out_dev, int board_size,

@@ -349,59 +349,37 @@ def test_player_read_device_feeds_replay_buffer():
     assert torch.allclose(batch['moves_prob'].sum(1), torch.ones(64, device='cuda'), atol=1e-5)
 
 
-@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1)))
+@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1), (11, 4100)))
 def test_tcgen05_conv3x3_matches_torch(n, N):
-    """az_nn_conv3x3 (csrc/az_tower.cuh: tcgen05 implicit GEMM over the
-    padded pre-swizzled layout, N = 192 tap stacking) against F.conv2d in
-    fp32 on the same bf16 inputs: bias, ReLU, residual; pad cells stay zero.
-    Tolerance = one bf16 rounding of the output (2^-8 relative + 1e-2)."""
+    """az_nn_conv3x3 (csrc/az_tower.cuh: tcgen05 implicit GEMM over the slab
+    layout, N = 192 tap stacking, TMEM accumulator ring) against F.conv2d in
+    fp32 on the same bf16 inputs: bias, ReLU, residual, in place; everything
+    that is not a real cell stays zero.  Tolerance = one bf16 rounding of the
+    output (2^-8 relative + 1e-2)."""
     import ctypes
     import torch.nn.functional as F
-    from azalea_b200 import _cabi
+    from azalea_b200 import _cabi, tower_layout as tl
     L = _cabi.lib()
-    halo = L.az_nn_tower_halo(n)
-    rpb = (n + 1) ** 2
-
-    def swz(t):
-        R = t.shape[0]
-        idx = torch.arange(8, device=t.device)[None, :] ^ (torch.arange(R, device=t.device)[:, None] & 7)
-        out = torch.empty_like(t.view(R, 8, 8))
-        out.scatter_(1, idx[:, :, None].expand(R, 8, 8), t.view(R, 8, 8))
-        return out.view(R, 64)
-
-    def unswz(t):
-        R = t.shape[0]
-        idx = torch.arange(8, device=t.device)[None, :] ^ (torch.arange(R, device=t.device)[:, None] & 7)
-        return torch.gather(t.view(R, 8, 8), 1, idx[:, :, None].expand(R, 8, 8)).reshape(R, 64)
-
-    def to_padded(x):
-        pd = torch.zeros(N, n + 1, n + 1, 64, dtype=x.dtype, device=x.device)
-        pd[:, :n, :n] = x
-        buf = torch.zeros(L.az_nn_tower_rows(n, N), 64, dtype=x.dtype, device=x.device)
-        buf[halo:halo + N * rpb] = pd.view(-1, 64)
-        return swz(buf)
-
+    assert L.az_nn_tower_rows(n, N) == tl.buffer_rows(n, N)
+    assert L.az_nn_tower_group(n) == tl.boards_per_group(n)
     torch.manual_seed(n)
     x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
     r = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
     w = (torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16)
     b = torch.randn(64, device='cuda') * 0.1
-    xp, rp = to_padded(x), to_padded(r)
-    wp = swz(w.permute(2, 3, 0, 1).reshape(9 * 64, 64).contiguous())
+    xp, rp, wp = tl.to_slabs(x), tl.to_slabs(r), tl.pack_conv_weights(w)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     for use_res in (False, True):
-        out = torch.full_like(xp, 3.0)
-        out[:halo] = 0
-        out[halo + N * rpb:] = 0
-        _cabi.check(L.az_nn_conv3x3(p(xp), p(wp), p(b), p(rp) if use_res else None, p(out), n, N, stream))
-        got = unswz(out)[halo:halo + N * rpb].view(N, n + 1, n + 1, 64).float()
+        out = rp.clone() if use_res else torch.zeros_like(xp)     # residual case runs in place
+        _cabi.check(L.az_nn_conv3x3(p(xp), p(wp), p(b), p(out) if use_res else None, p(out), n, N, stream))
+        got, rest = tl.from_slabs(out, n, N)
         want = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), b, padding=1)
         if use_res:
             want = want + r.permute(0, 3, 1, 2).float()
         want = F.relu(want).permute(0, 2, 3, 1)
-        assert ((got[:, :n, :n] - want).abs() <= want.abs() * 2 ** -8 + 1e-2).all()
-        assert float(got[:, n].abs().max()) == 0 and float(got[:, :, n].abs().max()) == 0
+        assert ((got.float() - want).abs() <= want.abs() * 2 ** -8 + 1e-2).all()
+        assert rest == 0.0
 
 
 def test_tcgen05_tower_matches_cudnn_tower():

@@ -3,7 +3,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 from azalea_b200 import _cabi
 L = _cabi.lib()
 n, N = 11, 40960
-H = L.az_nn_tower_halo(n)
 rows = L.az_nn_tower_rows(n, N)
 x = (torch.randn(rows, 64, device='cuda') * 0.5).to(torch.bfloat16)
 r = (torch.randn(rows, 64, device='cuda') * 0.5).to(torch.bfloat16)

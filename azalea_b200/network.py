@@ -82,10 +82,11 @@ class HexNetwork(nn.Module):
         self.encoder = nn.Embedding(3, 4)
         self.move_fc = nn.Linear(policy_chans * nn2, nn2)
         self._fast = None
-        # 'cudnn': the tower is twelve fused cuDNN calls (default);
-        # 'tcgen05': our implicit-GEMM kernel (csrc/az_tower.cuh), 64 channels only
+        # 'tcgen05' (default): the tower runs on our implicit-GEMM kernel
+        # (csrc/az_tower.cuh; 64 channels, bf16, board <= 19);
+        # 'cudnn': twelve fused cuDNN calls (also used for other widths)
         import os
-        self.tower = os.environ.get('AZALEA_B200_TOWER', 'cudnn')
+        self.tower = os.environ.get('AZALEA_B200_TOWER', 'tcgen05')
         nnet = sum(p.nelement() for p in self.parameters())
         nenc = sum(p.nelement() for p in self.encoder.parameters())
         logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)

@@ -43,17 +43,31 @@
 // global memory (16-byte chunk j of row R at chunk j ^ (R & 7)), so an input
 // slab plus its two neighbour rows is one contiguous 18 KB block.
 //
-// Roles (608 threads, one persistent CTA per SM, a contiguous range of board
+// (4) Nothing but MMAs on the issuing thread.  The tcgen05 pipe does not
+// queue ahead: every cycle the issuing thread spends on anything else
+// (barrier polls, descriptor arithmetic) is a cycle the tensor cores idle,
+// switching accumulators between consecutive MMAs costs ~33 cycles and a
+// commit ~29 (tools/probe/umma_gap.cu).  So two issuer warps alternate slabs:
+// while one issues its 12 back-to-back MMAs (one commit), the other waits for
+// the next slab's barriers and computes its descriptors, then takes over
+// through a named barrier.  The epilogue is two groups of eight warps on
+// alternate output slabs for the same reason: one slab's read -> convert ->
+// store chain is longer than a slab's MMA time.
+//
+// Roles (672 threads, one persistent CTA per SM, a contiguous range of board
 // groups per CTA):
-//   warps 0-15 epilogue: warp (quarter, quadrant) owns 16 channels of 32 rows
-//   warp 16    one thread issues tcgen05.mma
-//   warp 17    one thread streams input slabs through a 4-stage ring
-//   warp 18    one thread bulk-loads residual slabs into the staging tiles
+//   warps 0-7   epilogue group 0 (even output slabs): warp = (32 channels, 32 rows)
+//   warps 8-15  epilogue group 1 (odd output slabs)
+//   warps 16,17 MMA issuers (even / odd input slabs)
+//   warp 18     one thread streams input slabs through a 4-stage ring
+//   warp 19     one thread bulk-loads residual slabs into the staging tiles
+//   warp 20     one thread bulk-stores finished staging tiles
 #pragma once
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define AZT_C 64                    // channels = one 128-byte swizzle row
 #define AZT_ROW 128                 // bytes per row
@@ -63,9 +77,9 @@
 #define AZT_CHUNK_ROWS 144          // 8 + 128 + 8
 #define AZT_CHUNK_BYTES (AZT_CHUNK_ROWS * AZT_ROW)
 #define AZT_OUT_BYTES (128 * AZT_ROW)
-#define AZT_OUT_STAGES 4            // staging slabs: residual in, finished slab out
+#define AZT_OUT_STAGES 5            // staging slabs: residual in, finished slab out
 #define AZT_SMEM_BYTES (AZT_WBYTES + AZT_STAGES * AZT_CHUNK_BYTES + AZT_OUT_STAGES * AZT_OUT_BYTES)
-#define AZT_THREADS 608
+#define AZT_THREADS 672
 #define AZT_BLOCKS 8                // TMEM ring: 8 x 64 columns
 
 struct azt_params {
@@ -78,7 +92,7 @@ struct azt_params {
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
     int debug;              // probe only: 2 = skip the output stores, 4 = skip the epilogue after the
-                            // block retirement, 8 = skip the MMAs, 16 = skip the input loads
+                            // block retirement, 8 = skip the MMAs, 16 = skip the input loads, 128 = print clocks
 };
 
 __device__ __forceinline__ uint32_t azt_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +111,13 @@ __device__ __forceinline__ void azt_mbar_wait(uint64_t *bar, uint32_t parity)
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done) : "r"(azt_smem(bar)), "r"(parity) : "memory");
     }
+}
+
+__device__ __forceinline__ bool azt_elect()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ void azt_mbar_arrive(uint64_t *bar)
@@ -169,20 +190,28 @@ k_conv3x3(const azt_params p)
     uint8_t *s_w = smem;                                            // 72 KB
     uint8_t *s_in = smem + AZT_WBYTES;                              // ring of input slabs (+ 8 rows each side)
     uint8_t *s_out = s_in + AZT_STAGES * AZT_CHUNK_BYTES;           // staging slabs
-    __shared__ uint64_t bar_w, bar_in_full[AZT_STAGES], bar_in_empty[AZT_STAGES];
+    __shared__ uint64_t bar_w, bar_in_full[AZT_STAGES];
     __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7 (the MMA runs at most 7 slabs ahead)
     __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
-    __shared__ uint64_t bar_out_full[AZT_OUT_STAGES], bar_out_empty[AZT_OUT_STAGES];
+    __shared__ uint64_t bar_out_full[AZT_OUT_STAGES], bar_out_empty[AZT_OUT_STAGES], bar_out_done[AZT_OUT_STAGES];
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(16) float s_bias[AZT_C];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long dbg_c0 = 0, dbg_t0 = 0;
+    if ((p.debug & 128) && tid == 0) {
+        dbg_c0 = clock64();
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
+    }
     if (tid == 0) {
         azt_mbar_init(&bar_w, 1);
-        for (int i = 0; i < AZT_STAGES; i++) { azt_mbar_init(&bar_in_full[i], 1); azt_mbar_init(&bar_in_empty[i], 1); }
+        for (int i = 0; i < AZT_STAGES; i++) azt_mbar_init(&bar_in_full[i], 1);
         for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
-        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 512);
-        for (int i = 0; i < AZT_OUT_STAGES; i++) { azt_mbar_init(&bar_out_full[i], 1); azt_mbar_init(&bar_out_empty[i], 1); }
+        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
+        for (int i = 0; i < AZT_OUT_STAGES; i++) {
+            azt_mbar_init(&bar_out_full[i], 1); azt_mbar_init(&bar_out_empty[i], 1);
+            azt_mbar_init(&bar_out_done[i], 8);         // one arrival per warp of the group that wrote the slab
+        }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     if (tid < AZT_C) s_bias[tid] = p.bias[tid];
@@ -214,7 +243,23 @@ k_conv3x3(const azt_params p)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    if (warp == 18) {
+    if (warp == 20) {
+        // -------------------------------------------------------- storer --
+        if (lane == 0 && !(p.debug & 4)) {
+            for (int j = 0; j < nslabs; j++) {
+                const int sb = j % AZT_OUT_STAGES;
+                azt_mbar_wait(&bar_out_done[sb], (j / AZT_OUT_STAGES) & 1);
+                if (!(p.debug & 2))
+                    azt_bulk_s2g(p.out + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
+                                 AZT_OUT_BYTES);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // the previous store has finished reading its staging slab: hand it back
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                if (j >= 1) azt_mbar_arrive(&bar_out_empty[(j - 1) % AZT_OUT_STAGES]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp == 19) {
         // ----------------------------------------------- residual loader --
         if (RESID && lane == 0 && !(p.debug & 4)) {
             for (int j = 0; j < nslabs; j++) {
@@ -225,14 +270,15 @@ k_conv3x3(const azt_params p)
                              p.resid + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, AZT_OUT_BYTES, &bar_out_full[sb]);
             }
         }
-    } else if (warp == 17) {
+    } else if (warp == 18) {
         // -------------------------------------------------- input loader --
         if (lane == 0) {
             azt_mbar_expect_tx(&bar_w, AZT_WBYTES);
             for (int t = 0; t < 9; t++) azt_bulk_g2s(s_w + t * 8192, p.w + t * 8192, 8192, &bar_w);
             for (int j = 0; j < nslabs; j++) {
                 const int st = j % AZT_STAGES;
-                azt_mbar_wait(&bar_in_empty[st], ((j / AZT_STAGES) & 1) ^ 1);
+                // the stage is free once the MMAs of the slab that used it last have retired
+                if (j >= AZT_STAGES) azt_mbar_wait(&bar_mma_done[(j - AZT_STAGES) & 7], ((j - AZT_STAGES) >> 3) & 1);
                 if (p.debug & 16) { azt_mbar_arrive(&bar_in_full[st]); continue; }
                 // slab rows plus 8 rows on each side: global rows [128 q, 128 q + 144)
                 azt_mbar_expect_tx(&bar_in_full[st], AZT_CHUNK_BYTES);
@@ -240,118 +286,149 @@ k_conv3x3(const azt_params p)
                              AZT_CHUNK_BYTES, &bar_in_full[st]);
             }
         }
-    } else if (warp == 16) {
-        // --------------------------------------------------- MMA issuer --
-        if (lane == 0) {
-            azt_mbar_wait(&bar_w, 0);
-            const uint32_t b_base = azt_smem(s_w);
-            int entered = -1;                       // highest output slab whose ring block has been entered
-            for (int j = 0, y = 0; j < nslabs; j++, y = (y + 1 == n ? 0 : y + 1)) {
-                const int st = j % AZT_STAGES;
-                azt_mbar_wait(&bar_in_full[st], (j / AZT_STAGES) & 1);
-                // input slab j feeds output slabs j+1 (dy 0), j (dy 1), j-1 (dy 2) of the same group
-                const int dy0 = y + 1 < n ? 0 : 1, dy1 = y > 0 ? 2 : 1;
-                const int top = j + 1 - dy0;
-                // a block entered for a new output slab t: its previous tenant t-8 must have been retired
-                for (int t = entered + 1; t <= top; t++)
-                    if (t >= 8) azt_mbar_wait(&bar_blk_free[AZT_RING(t)], ((t >> 3) - 1) & 1);
-                entered = top > entered ? top : entered;
-                asm volatile("tcgen05.fence::after_thread_sync;");
-                const int blk = AZT_RING(top), nb = dy1 - dy0 + 1;
-                const int first = nb < 8 - blk ? nb : 8 - blk, second = nb - first;     // split where the ring wraps
-                const uint32_t d0 = tmem + blk * 64, i0 = AZT_IDESC(first), i1 = AZT_IDESC(second);
-                const uint32_t a_base = azt_smem(s_in + st * AZT_CHUNK_BYTES) + 7 * AZT_ROW;   // row l-1 of the slab
-                const uint32_t b_rows = b_base + dy0 * 64 * AZT_ROW;
+    } else if (warp >= 16) {
+        // -------------------------------------------------- MMA issuers --
+        // Warp 16 issues the even slabs, warp 17 the odd ones.  A whole warp runs the loop
+        // (uniform control flow keeps descriptors in uniform registers: the 12 MMAs of a
+        // slab are back-to-back instructions); one elected lane issues.  The turn passes
+        // through named barriers 3 (-> even) and 4 (-> odd).
+        const int w = warp - 16;
+        azt_mbar_wait(&bar_w, 0);
+        const uint64_t db_base = azt_desc(azt_smem(s_w));
+        if (w == 1 && nslabs > 0) asm volatile("bar.arrive 3, 64;" ::: "memory");   // slab 0 has the first turn
+        for (int j = w, y = w % n; j < nslabs; j += 2, y = (y + 2) % n) {
+            const int st = j % AZT_STAGES;
+            // input slab j feeds output slabs j+1 (dy 0), j (dy 1), j-1 (dy 2) of the same group
+            const int dy0 = y + 1 < n ? 0 : 1, dy1 = y > 0 ? 2 : 1;
+            const int top = j + 1 - dy0;
+            // highest output slab entered by the slabs before this one
+            const int entered = j == 0 ? -1 : (y == 0 ? j - 1 : j);
+            azt_mbar_wait(&bar_in_full[st], (j / AZT_STAGES) & 1);
+            // a block entered for a new output slab t: its previous tenant t-8 must have been retired
+            for (int t = entered + 1; t <= top; t++)
+                if (t >= 8) azt_mbar_wait(&bar_blk_free[AZT_RING(t)], ((t >> 3) - 1) & 1);
+            const int blk = AZT_RING(top), nb = dy1 - dy0 + 1;
+            const int first = nb < 8 - blk ? nb : 8 - blk, second = nb - first;     // split where the ring wraps
+            const uint32_t d0 = tmem + blk * 64, i0 = AZT_IDESC(first), i1 = AZT_IDESC(second);
+            // descriptors advance in 16-byte units: one row = 8, one K step (32 B) = 2
+            const uint64_t da0 = azt_desc(azt_smem(s_in + st * AZT_CHUNK_BYTES) + 7 * AZT_ROW);    // row l-1 of the slab
+            const uint64_t db0 = db_base + (uint64_t)(dy0 * 64 * (AZT_ROW / 16));
+            const uint64_t db1 = db0 + (uint64_t)(first * 64 * (AZT_ROW / 16));
+            // take the turn: the other warp has issued slab j-1
+            if (w == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (azt_elect()) {
+                if (!(p.debug & 8)) {
+                    if (second == 0) {
 #pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    if (p.debug & 8) break;
+                        for (int dx = 0; dx < 3; dx++)
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const uint64_t da = azt_desc(a_base + dx * AZT_ROW + k * 32);
-                        const uint32_t b_dx = b_rows + dx * (192 * AZT_ROW) + k * 32;
-                        azt_mma(d0, da, azt_desc(b_dx), i0);
-                        if (second) azt_mma(tmem, da, azt_desc(b_dx + first * 64 * AZT_ROW), i1);
+                            for (int k = 0; k < 4; k++)
+                                azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
+                    } else {
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
+                                azt_mma(tmem, da0 + (dx * 8 + k * 2), db1 + (dx * 192 * 8 + k * 2), i1);
+                            }
                     }
                 }
+                // one commit per slab: output slabs wait for it, and so does the input stage
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                              ::"r"(azt_smem(&bar_mma_done[j & 7])) : "memory");
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(azt_smem(&bar_in_empty[st])) : "memory");
+            }
+            __syncwarp();
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            if (j + 1 < nslabs) {
+                if (w == 0) asm volatile("bar.arrive 4, 64;" ::: "memory");
+                else asm volatile("bar.arrive 3, 64;" ::: "memory");
             }
         }
     } else {
         // ----------------------------------------------------- epilogue --
-        // thread = TMEM lane = row l of the slab; this warp's 16 channels
-        const int cq = warp >> 2, wq = warp & 3;
+        // group = warp >> 3 takes the output slabs j = group (mod 2); inside a group a warp
+        // owns 32 channels (half) of the 32 rows its TMEM lane quadrant holds:
+        // thread = TMEM lane = row l of the slab
+        const int grp = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
         const int l = wq * 32 + lane;
         const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
         const uint32_t keep = real ? 0xffffffffu : 0u;
         const int sw = l & 7;                                       // == R & 7 (8 + 128 q + l)
-        float bias[16];
-#pragma unroll
-        for (int q = 0; q < 16; q++) bias[q] = s_bias[cq * 16 + q];
-        for (int j = 0, y = 0; j < nslabs; j++, y = (y + 1 == n ? 0 : y + 1)) {
+        for (int j = grp, y = grp % n; j < nslabs; j += 2, y = (y + 2) % n) {
+            const int sb = j % AZT_OUT_STAGES;
+            uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
+            if (!(p.debug & 4)) {
+                // the staging slab holds the residual (RESID) or must have been
+                // drained by the bulk store that used it last
+                if (RESID) azt_mbar_wait(&bar_out_full[sb], (j / AZT_OUT_STAGES) & 1);
+                else azt_mbar_wait(&bar_out_empty[sb], ((j / AZT_OUT_STAGES) & 1) ^ 1);
+            }
             // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
             const int last = y + 1 < n ? j + 1 : j;
             azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;");
             const int blk = AZT_RING(j);
-            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u + (uint32_t)cq * 16u;
-            uint32_t acc[16];
-            AZT_TMEM_LD16(acc, ta);
-            asm volatile("tcgen05.wait::ld.sync.aligned;");
-            // retire the block: zero it for its next output slab and hand it back
-            azt_tmem_zero16(ta);
-            asm volatile("tcgen05.wait::st.sync.aligned;");
-            asm volatile("tcgen05.fence::before_thread_sync;");
-            azt_mbar_arrive(&bar_blk_free[blk]);
-            if (p.debug & 4) continue;
-            const int sb = j % AZT_OUT_STAGES;
-            uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
-            // the staging slab holds the residual (RESID) or must have been
-            // drained by the bulk store that used it last
-            if (RESID) azt_mbar_wait(&bar_out_full[sb], (j / AZT_OUT_STAGES) & 1);
-            else azt_mbar_wait(&bar_out_empty[sb], ((j / AZT_OUT_STAGES) & 1) ^ 1);
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u + (uint32_t)half * 32u;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float f[8];
+                uint32_t acc[16];
+                AZT_TMEM_LD16(acc, ta + h * 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                azt_tmem_zero16(ta + h * 16);       // retire: zero for the block's next output slab
+                if (p.debug & 4) continue;
 #pragma unroll
-                for (int q = 0; q < 8; q++) f[q] = __uint_as_float(acc[h * 8 + q]) + bias[h * 8 + q];
-                if (RESID) {
-                    const uint4 r = srow[(cq * 2 + h) ^ sw];
-                    const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+                for (int g = 0; g < 2; g++) {
+                    const int c8 = half * 4 + h * 2 + g;            // 8-channel chunk of the row
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8 + 4]);
+                    float f[8];
+                    f[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
+                    if (RESID) {
+                        const uint4 r = srow[c8 ^ sw];
+                        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                        }
+                    }
+                    uint32_t ow[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        f[2 * q] += __uint_as_float(rw[q] << 16);
-                        f[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
+                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
                     }
+                    srow[c8 ^ sw] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
-                uint32_t ow[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                    ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
-                }
-                srow[(cq * 2 + h) ^ sw] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
             }
-            // staging slab complete: one thread sends it to global memory
+            // hand the ring block back
+            asm volatile("tcgen05.wait::st.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
+            if (p.debug & 4) continue;
+            // staging slab complete: the storer sends it to global memory
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 1, 512;" ::: "memory");
-            if (tid == 0) {
-                if (!(p.debug & 2))
-                    azt_bulk_s2g(p.out + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
-                                 AZT_OUT_BYTES);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // the previous slab's store has finished reading its staging slab
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                if (j > 0) azt_mbar_arrive(&bar_out_empty[(j - 1) % AZT_OUT_STAGES]);
-            }
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);
         }
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 #undef AZT_RING
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if ((p.debug & 128) && tid == 0 && blockIdx.x == 0) {
+        long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        const long long c = clock64() - dbg_c0;
+        printf("block %d: %lld cycles in %lld ns = %.3f GHz, %d slabs, %.1f cycles per slab\n", blockIdx.x, c, t1 - dbg_t0,
+               (double)c / (double)(t1 - dbg_t0), nslabs, (double)c / nslabs);
+    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }

@@ -938,6 +938,23 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
         cell_stride < board_size * board_size)
         return AZ_E_INVALID;
     if (num_boards == 0) return AZ_OK;
+    if (padded_layout) {
+        const int bpg = 128 / (board_size + 1);
+        const size_t smem = AZ_STEM_SLAB_SMEM(board_size, bpg);
+        static bool attr_set = false;
+        if (!attr_set) {
+            int rc = az_check(cudaFuncSetAttribute(k_nn_stem_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   AZ_STEM_SLAB_SMEM(19, 6)));
+            if (rc != AZ_OK) return rc;
+            attr_set = true;
+        }
+        long long blocks = (num_boards + bpg - 1) / bpg;
+        if (blocks > 148 * 4) blocks = 148 * 4;
+        k_nn_stem_slab<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+            cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
+            bias_dev, (uint16_t *)out_dev);
+        return az_check(cudaGetLastError());
+    }
     const int pnn = (board_size + 2) * (board_size + 2);
     const int nn = board_size * board_size;
     const size_t smem = (size_t)36 * channels * 2 + (size_t)((nn + 1) & ~1) * 2 +
@@ -962,6 +979,16 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
     if (((channels >> 3) & ((channels >> 3) - 1)) || (channels >> 3) < 4)
         return AZ_E_UNSUPPORTED;               /* lanes per position: power of two, >= heads/2 */
     if (positions == 0) return AZ_OK;
+    if (padded_board_size) {
+        const int n = padded_board_size, bpg = 128 / (n + 1);
+        if (n < 2 || n > 19 || positions % (n * n)) return AZ_E_INVALID;
+        const long long boards = positions / (n * n);
+        long long blocks = (boards + bpg - 1) / bpg * n;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        k_nn_heads_slab<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const uint16_t *)x_dev, boards, n, w_dev, b_dev, (uint16_t *)out_dev);
+        return az_check(cudaGetLastError());
+    }
     long long blocks = (positions * (channels >> 3) + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_nn_heads<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(

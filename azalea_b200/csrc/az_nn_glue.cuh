@@ -180,3 +180,151 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
         }
     }
 }
+
+// ---------------------------------------------------------------------------
+// Slab-layout versions (the tcgen05 tower, az_tower.cuh; C == 64).  Both walk
+// the activation buffer in memory order -- one block per 128-row slab -- so no
+// thread ever divides a position index, and every warp access is 512
+// contiguous bytes.
+//
+// k_nn_stem_slab: a block takes a whole board group (bpg boards, n slabs).  The
+// three horizontal taps of a kernel row are one lookup: code = v(x-1) + 4 v(x)
+// + 16 v(x+1) indexes T3[dy][code][c] = sum_dx T[dy*3+dx][v_dx][c] (fp32,
+// 48 KB of shared memory, built once per block), so a 16-byte output chunk is
+// 3 code bytes + 6 LDS.128 + 24 FADD instead of nine table lookups.
+#define AZ_STEM_SLAB_SMEM(n, bpg) (3 * 64 * 64 * 4 + (((bpg) * ((n) + 2) * (n) + 15) & ~15))
+
+__global__ void __launch_bounds__(256)
+k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
+               const uint16_t *__restrict__ table, const float *__restrict__ bias,
+               uint16_t *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *t3 = reinterpret_cast<float *>(smem_raw);                    // [3 dy][64 codes][64 c]
+    uint8_t *scode = smem_raw + 3 * 64 * 64 * 4;                        // [bpg][n + 2 rows][n]
+    const int pn1 = n + 1, bpg = 128 / pn1;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * 64 * 64; i += 256) {
+        const int c = i & 63, code = (i >> 6) & 63, dy = i >> 12;
+        float acc = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++)
+            acc += __uint_as_float((uint32_t)table[((dy * 3 + dx) * 4 + ((code >> (2 * dx)) & 3)) * 64 + c] << 16);
+        t3[i] = acc;
+    }
+    // this thread's chunk of the rows l = (tid >> 3) + 32 i; the physical chunk tid & 7 holds
+    // the logical chunk cg (swizzle: the row's low three bits are those of l)
+    const int cg = (tid & 7) ^ ((tid >> 3) & 7);
+    float b8[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) b8[k] = bias[cg * 8 + k];
+    int bl[4], bx[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int l = (tid >> 3) + 32 * i;
+        bl[i] = l / pn1;
+        bx[i] = l - bl[i] * pn1;
+        if (bl[i] >= bpg || bx[i] >= n) bl[i] = -1;                     // pad cell: stays zero
+    }
+    const long long groups = (N + bpg - 1) / bpg;
+    for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
+        __syncthreads();
+        // codes of the group's boards, with an off-board row above and below
+        for (int i = tid; i < bpg * (n + 2) * n; i += 256) {
+            const int b = i / ((n + 2) * n), r = (i / n) % (n + 2) - 1, c = i % n;
+            int code = 3 + 4 * 3 + 16 * 3;
+            const long long board = g * bpg + b;
+            if (board < N && r >= 0 && r < n) {
+                const int8_t *row = cells + board * cell_stride + r * n;
+                code = (c > 0 ? row[c - 1] : 3) + 4 * row[c] + 16 * (c + 1 < n ? row[c + 1] : 3);
+            }
+            scode[i] = (uint8_t)code;
+        }
+        __syncthreads();
+        for (int y = 0; y < n; y++) {
+            uint16_t *slab = out + (8 + (g * n + y) * 128) * 64;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (bl[i] < 0 || g * bpg + bl[i] >= N) continue;
+                const uint8_t *sc = scode + (bl[i] * (n + 2) + y) * n + bx[i];   // row y-1 of the padded codes
+                float acc[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] = b8[k];
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++) {
+                    const float4 *t = reinterpret_cast<const float4 *>(t3 + (dy * 64 + sc[dy * n]) * 64 + cg * 8);
+                    const float4 u = t[0], v = t[1];
+                    acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
+                    acc[4] += v.x; acc[5] += v.y; acc[6] += v.z; acc[7] += v.w;
+                }
+                uint4 o;
+                o.x = az_pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+                o.y = az_pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+                o.z = az_pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+                o.w = az_pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+                reinterpret_cast<uint4 *>(slab)[tid + 256 * i] = o;
+            }
+        }
+    }
+}
+
+// k_nn_heads_slab: a block takes one slab per step; thread = (row l = (tid >> 3) + 32 i, 16-byte
+// chunk tid & 7), the eight lanes of a row reduce by xor-shuffles as in k_nn_heads.
+template <int H>
+__global__ void __launch_bounds__(256, 3)
+k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float *__restrict__ w,
+                const float *__restrict__ b, uint16_t *__restrict__ out)
+{
+    const int tid = threadIdx.x, cp = tid & 7;
+    const int cg = cp ^ ((tid >> 3) & 7);               // logical channel chunk this thread loads
+    const int nn = n * n, pn1 = n + 1, bpg = 128 / pn1;
+    float wr[H][8], br[H];
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        br[h] = b[h];
+#pragma unroll
+        for (int k = 0; k < 8; k++) wr[h][k] = w[h * 64 + cg * 8 + k];
+    }
+    int bl[4], off[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int l = (tid >> 3) + 32 * i;
+        bl[i] = l / pn1;
+        const int bx = l - bl[i] * pn1;
+        off[i] = (bl[i] * nn + bx) * H;
+        if (bl[i] >= bpg || bx >= n) bl[i] = -1;
+    }
+    const long long slabs = (N + bpg - 1) / bpg * n;
+    for (long long q = blockIdx.x; q < slabs; q += gridDim.x) {
+        const long long g = q / n;
+        const int y = (int)(q - g * n);
+        const uint4 *slab = reinterpret_cast<const uint4 *>(x + (8 + q * 128) * 64);
+        uint4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = slab[tid + 256 * i];
+        uint16_t *obase = out + (g * bpg * nn + (long long)y * n) * H;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float f[8], acc[H];
+            az_bf16x8_to_f32(v[i], f);
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                acc[h] = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[h] = fmaf(f[k], wr[h][k], acc[h]);
+            }
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+                for (int h = 0; h < H; h++) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
+            if (bl[i] >= 0 && g * bpg + bl[i] < N && cp < H / 2) {
+                // lane cp of the row writes outputs 2cp, 2cp+1
+                float lo = 0.f, hi = 0.f;
+#pragma unroll
+                for (int h = 0; h < H; h += 2)
+                    if (cp == h / 2) { lo = acc[h] + br[h]; hi = acc[h + 1] + br[h + 1]; }
+                reinterpret_cast<uint32_t *>(obase + off[i])[cp] = az_pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+            }
+        }
+    }
+}

@@ -281,6 +281,51 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
     assert (got_lp - want_lp).abs().mean() < 0.02
 
 
+@pytest.mark.parametrize('n,N', ((11, 257), (19, 13), (7, 1000), (5, 3)))
+def test_evaluator_glue_kernels_slab_layout(n, N):
+    """The slab-layout stem and heads (k_nn_stem_slab / k_nn_heads_slab, the
+    two ends of the tcgen05 tower) against the plain-layout kernels on the
+    same inputs.  Summation order differs, so outputs may differ by one bf16
+    rounding (rel 2^-7 + abs 1e-3); everything that is not a board cell stays
+    zero."""
+    import ctypes
+    from azalea_b200 import _cabi, tower_layout as tl
+    from azalea_b200.network import HexNetwork
+    torch.manual_seed(n)
+    net = HexNetwork(n, 1, 64).eval().cuda()
+    net.prepare_inference(torch.bfloat16)
+    f = net._fast
+    nn = n * n
+    cs = (nn + 15) & ~15
+    cells = torch.zeros(N, cs, dtype=torch.int8, device='cuda')
+    cells[:, :nn] = torch.randint(0, 3, (N, nn), device='cuda', dtype=torch.int8)
+    L = _cabi.lib()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    plain = torch.empty(N, n, n, 64, dtype=torch.bfloat16, device='cuda')
+    slab = torch.zeros(tl.buffer_rows(n, N), 64, dtype=torch.bfloat16, device='cuda')
+    for out, padded in ((plain, 0), (slab, 1)):
+        _cabi.check(L.az_nn_stem(p(cells), cs, n, N, p(f['stem_table']), p(f['stem_bias']),
+                                 p(out), 64, padded, stream))
+    got, rest = tl.from_slabs(slab, n, N)
+    bpg = tl.boards_per_group(n)
+    assert rest == 0.0
+    assert ((got.float() - plain.float()).abs() <= plain.float().abs() * 2 ** -7 + 1e-3).all()
+    # unused board slots of the last group are never written by the stem
+    full = tl.from_slabs(slab, n, (N + bpg - 1) // bpg * bpg)[0]
+    assert float(full[N:].float().abs().sum()) == 0.0
+    # heads
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.7).to(torch.bfloat16)
+    h_plain = torch.empty(N * nn, 6, dtype=torch.bfloat16, device='cuda')
+    h_slab = torch.full((N * nn + 7, 6), 7.0, dtype=torch.bfloat16, device='cuda')
+    _cabi.check(L.az_nn_heads(p(x), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_plain), 64, 6, 0, stream))
+    _cabi.check(L.az_nn_heads(p(tl.to_slabs(x)), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_slab),
+                              64, 6, n, stream))
+    assert (h_slab[N * nn:] == 7.0).all()           # nothing written past the last board
+    a, b = h_slab[:N * nn].float(), h_plain.float()
+    assert ((a - b).abs() <= b.abs() * 2 ** -7 + 1e-3).all()
+
+
 def test_device_replay_buffer_collate_matches_host_format():
     """DeviceReplayBuffer.sample == prep.torch_batch_replays over the same
     rows (prep.py:24-39,70-86): boards, ascending zero-padded legal moves,

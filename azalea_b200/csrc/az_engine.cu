@@ -949,7 +949,7 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
             attr_set = true;
         }
         long long blocks = (num_boards + bpg - 1) / bpg;
-        if (blocks > 148 * 4) blocks = 148 * 4;
+        if (blocks > 148 * 6) blocks = 148 * 6;
         k_nn_stem_slab<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
             cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
             bias_dev, (uint16_t *)out_dev);

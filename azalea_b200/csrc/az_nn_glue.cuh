@@ -189,10 +189,11 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
 //
 // k_nn_stem_slab: a block takes a whole board group (bpg boards, n slabs).  The
 // three horizontal taps of a kernel row are one lookup: code = v(x-1) + 4 v(x)
-// + 16 v(x+1) indexes T3[dy][code][c] = sum_dx T[dy*3+dx][v_dx][c] (fp32,
-// 48 KB of shared memory, built once per block), so a 16-byte output chunk is
-// 3 code bytes + 6 LDS.128 + 24 FADD instead of nine table lookups.
-#define AZ_STEM_SLAB_SMEM(n, bpg) (3 * 64 * 64 * 4 + (((bpg) * ((n) + 2) * (n) + 15) & ~15))
+// + 16 v(x+1) indexes T3[dy][code][c] = sum_dx T[dy*3+dx][v_dx][c] (bf16, 24 KB
+// of shared memory, built once per block), and the three codes of a cell are
+// one packed word, so a 16-byte output chunk is 1 LDS.32 + 3 conflict-free
+// LDS.128 + 24 FADD instead of nine byte loads and nine table lookups.
+#define AZ_STEM_SLAB_SMEM(n, bpg) (3 * 64 * 64 * 2 + (bpg) * (n) * (n) * 4 + (((bpg) * ((n) + 2) * ((n) + 2) + 15) & ~15))
 
 __global__ void __launch_bounds__(256)
 k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
@@ -200,9 +201,10 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
                uint16_t *__restrict__ out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *t3 = reinterpret_cast<float *>(smem_raw);                    // [3 dy][64 codes][64 c]
-    uint8_t *scode = smem_raw + 3 * 64 * 64 * 4;                        // [bpg][n + 2 rows][n]
-    const int pn1 = n + 1, bpg = 128 / pn1;
+    uint16_t *t3 = reinterpret_cast<uint16_t *>(smem_raw);              // [3 dy][64 codes][64 c]
+    uint32_t *scode = reinterpret_cast<uint32_t *>(smem_raw + 3 * 64 * 64 * 2);      // [bpg][n][n]
+    const int pn = n + 2, pn1 = n + 1, bpg = 128 / pn1;
+    int8_t *scell = reinterpret_cast<int8_t *>(scode + bpg * n * n);    // [bpg][n + 2][n + 2]
     const int tid = threadIdx.x;
     for (int i = tid; i < 3 * 64 * 64; i += 256) {
         const int c = i & 63, code = (i >> 6) & 63, dy = i >> 12;
@@ -210,7 +212,7 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
 #pragma unroll
         for (int dx = 0; dx < 3; dx++)
             acc += __uint_as_float((uint32_t)table[((dy * 3 + dx) * 4 + ((code >> (2 * dx)) & 3)) * 64 + c] << 16);
-        t3[i] = acc;
+        t3[i] = __bfloat16_as_ushort(__float2bfloat16_rn(acc));
     }
     // this thread's chunk of the rows l = (tid >> 3) + 32 i; the physical chunk tid & 7 holds
     // the logical chunk cg (swizzle: the row's low three bits are those of l)
@@ -218,27 +220,35 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
     float b8[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) b8[k] = bias[cg * 8 + k];
-    int bl[4], bx[4];
+    int bl[4], co[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int l = (tid >> 3) + 32 * i;
         bl[i] = l / pn1;
-        bx[i] = l - bl[i] * pn1;
-        if (bl[i] >= bpg || bx[i] >= n) bl[i] = -1;                     // pad cell: stays zero
+        const int bx = l - bl[i] * pn1;
+        co[i] = bl[i] * n * n + bx;                                     // + y * n: this cell's code word
+        if (bl[i] >= bpg || bx >= n) bl[i] = -1;                        // pad cell: stays zero
     }
     const long long groups = (N + bpg - 1) / bpg;
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         __syncthreads();
-        // codes of the group's boards, with an off-board row above and below
-        for (int i = tid; i < bpg * (n + 2) * n; i += 256) {
-            const int b = i / ((n + 2) * n), r = (i / n) % (n + 2) - 1, c = i % n;
-            int code = 3 + 4 * 3 + 16 * 3;
+        // the group's boards with a border of "off board" cells (value 3: zero table rows)
+        for (int i = tid; i < bpg * pn * pn; i += 256) {
+            const int b = i / (pn * pn), r = (i / pn) % pn - 1, c = i % pn - 1;
             const long long board = g * bpg + b;
-            if (board < N && r >= 0 && r < n) {
-                const int8_t *row = cells + board * cell_stride + r * n;
-                code = (c > 0 ? row[c - 1] : 3) + 4 * row[c] + 16 * (c + 1 < n ? row[c + 1] : 3);
-            }
-            scode[i] = (uint8_t)code;
+            int8_t v = 3;
+            if (board < N && r >= 0 && r < n && c >= 0 && c < n) v = cells[board * cell_stride + r * n + c];
+            scell[i] = v;
+        }
+        __syncthreads();
+        for (int i = tid; i < bpg * n * n; i += 256) {
+            const int b = i / (n * n), r = (i / n) % n, c = i % n;
+            const int8_t *sc = scell + (b * pn + r) * pn + c;           // top-left neighbour
+            uint32_t word = 0;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+                word |= (uint32_t)(sc[dy * pn] + 4 * sc[dy * pn + 1] + 16 * sc[dy * pn + 2]) << (8 * dy);
+            scode[i] = word;
         }
         __syncthreads();
         for (int y = 0; y < n; y++) {
@@ -246,16 +256,17 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (bl[i] < 0 || g * bpg + bl[i] >= N) continue;
-                const uint8_t *sc = scode + (bl[i] * (n + 2) + y) * n + bx[i];   // row y-1 of the padded codes
+                const uint32_t word = scode[co[i] + y * n];
                 float acc[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) acc[k] = b8[k];
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++) {
-                    const float4 *t = reinterpret_cast<const float4 *>(t3 + (dy * 64 + sc[dy * n]) * 64 + cg * 8);
-                    const float4 u = t[0], v = t[1];
-                    acc[0] += u.x; acc[1] += u.y; acc[2] += u.z; acc[3] += u.w;
-                    acc[4] += v.x; acc[5] += v.y; acc[6] += v.z; acc[7] += v.w;
+                    const uint4 tv = *reinterpret_cast<const uint4 *>(t3 + (dy * 64 + ((word >> (8 * dy)) & 63)) * 64 + cg * 8);
+                    float f[8];
+                    az_bf16x8_to_f32(tv, f);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) acc[k] += f[k];
                 }
                 uint4 o;
                 o.x = az_pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
@@ -268,63 +279,77 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
     }
 }
 
-// k_nn_heads_slab: a block takes one slab per step; thread = (row l = (tid >> 3) + 32 i, 16-byte
-// chunk tid & 7), the eight lanes of a row reduce by xor-shuffles as in k_nn_heads.
+// k_nn_heads_slab: the 64 -> H (<= 8) projection of a slab on mma.sync tensor cores: a warp
+// takes 16 rows, four m16n8k16 steps cover the 64 channels.  No shared memory and no shuffles:
+// the dot product does not care about the order of k, so thread (g = lane / 4, t = lane % 4)
+// simply declares the 16 channels of the two 16-byte chunks it loads (logical chunks t and
+// t + 4 of rows g and g + 8) to be its k slots, and holds the weights of the same channels
+// in its B fragments.  Weights are split into bf16 hi + lo parts (two MMAs per step), so the
+// result has fp32-weight accuracy like k_nn_heads.
+__device__ __forceinline__ void az_mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 template <int H>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float *__restrict__ w,
                 const float *__restrict__ b, uint16_t *__restrict__ out)
 {
-    const int tid = threadIdx.x, cp = tid & 7;
-    const int cg = cp ^ ((tid >> 3) & 7);               // logical channel chunk this thread loads
+    static_assert(H <= 8 && (H & 1) == 0, "heads fit one n = 8 MMA tile");
+    const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int nn = n * n, pn1 = n + 1, bpg = 128 / pn1;
-    float wr[H][8], br[H];
+    // B fragments of column (head) g for the four k steps: step s covers channels
+    // chunk * 8 + (s & 1) * 4 + {0..3} of chunk = t (s < 2) or t + 4
+    uint32_t bhi[4][2], blo[4][2];
 #pragma unroll
-    for (int h = 0; h < H; h++) {
-        br[h] = b[h];
+    for (int s = 0; s < 4; s++)
 #pragma unroll
-        for (int k = 0; k < 8; k++) wr[h][k] = w[h * 64 + cg * 8 + k];
+        for (int r = 0; r < 2; r++) {
+            const int k0 = ((s < 2 ? t : t + 4) * 8) + (s & 1) * 4 + 2 * r;
+            const float w0 = g < H ? w[g * 64 + k0] : 0.f, w1 = g < H ? w[g * 64 + k0 + 1] : 0.f;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+            bhi[s][r] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            blo[s][r] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+    const float bias0 = 2 * t < H ? b[2 * t] : 0.f, bias1 = 2 * t < H ? b[2 * t + 1] : 0.f;
+    // this thread's two rows of every slab (l & 7 == g for both: same swizzle)
+    int lrow[2], off[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        lrow[r] = (tid >> 5) * 16 + g + 8 * r;
+        const int bl = lrow[r] / pn1, bx = lrow[r] - bl * pn1;
+        off[r] = (bl * nn + bx) * H;
+        if (bl >= bpg || bx >= n) off[r] = -1;                           // pad cell
+        else if (2 * t >= H) off[r] = -1;                                // columns H..7 are padding
     }
-    int bl[4], off[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int l = (tid >> 3) + 32 * i;
-        bl[i] = l / pn1;
-        const int bx = l - bl[i] * pn1;
-        off[i] = (bl[i] * nn + bx) * H;
-        if (bl[i] >= bpg || bx >= n) bl[i] = -1;
-    }
+    const int c0 = t ^ g, c1 = (t + 4) ^ g;                              // physical chunks of logical t, t + 4
     const long long slabs = (N + bpg - 1) / bpg * n;
     for (long long q = blockIdx.x; q < slabs; q += gridDim.x) {
-        const long long g = q / n;
-        const int y = (int)(q - g * n);
+        const long long grp = q / n;
+        const int y = (int)(q - grp * n);
         const uint4 *slab = reinterpret_cast<const uint4 *>(x + (8 + q * 128) * 64);
-        uint4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = slab[tid + 256 * i];
-        uint16_t *obase = out + (g * bpg * nn + (long long)y * n) * H;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float f[8], acc[H];
-            az_bf16x8_to_f32(v[i], f);
-#pragma unroll
-            for (int h = 0; h < H; h++) {
-                acc[h] = 0.f;
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[h] = fmaf(f[k], wr[h][k], acc[h]);
-            }
-#pragma unroll
-            for (int o = 1; o < 8; o <<= 1)
-#pragma unroll
-                for (int h = 0; h < H; h++) acc[h] += __shfl_xor_sync(0xffffffffu, acc[h], o);
-            if (bl[i] >= 0 && g * bpg + bl[i] < N && cp < H / 2) {
-                // lane cp of the row writes outputs 2cp, 2cp+1
-                float lo = 0.f, hi = 0.f;
-#pragma unroll
-                for (int h = 0; h < H; h += 2)
-                    if (cp == h / 2) { lo = acc[h] + br[h]; hi = acc[h + 1] + br[h + 1]; }
-                reinterpret_cast<uint32_t *>(obase + off[i])[cp] = az_pack_bf16x2(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
-            }
+        const uint4 a00 = slab[lrow[0] * 8 + c0], a01 = slab[lrow[0] * 8 + c1];
+        const uint4 a10 = slab[lrow[1] * 8 + c0], a11 = slab[lrow[1] * 8 + c1];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+            const uint32_t f0[4] = {a00.x, a10.x, a00.y, a10.y}, f1[4] = {a00.z, a10.z, a00.w, a10.w};
+            const uint32_t f2[4] = {a01.x, a11.x, a01.y, a11.y}, f3[4] = {a01.z, a11.z, a01.w, a11.w};
+            az_mma_bf16_16816(acc, f0, bhi[0]); az_mma_bf16_16816(acc, f0, blo[0]);
+            az_mma_bf16_16816(acc, f1, bhi[1]); az_mma_bf16_16816(acc, f1, blo[1]);
+            az_mma_bf16_16816(acc, f2, bhi[2]); az_mma_bf16_16816(acc, f2, blo[2]);
+            az_mma_bf16_16816(acc, f3, bhi[3]); az_mma_bf16_16816(acc, f3, blo[3]);
         }
+        uint16_t *obase = out + (grp * bpg * nn + (long long)y * n) * H;
+        const long long left = (N - grp * bpg) * (long long)nn * H;     // elements of boards that exist
+#pragma unroll
+        for (int r = 0; r < 2; r++)
+            if (off[r] >= 0 && off[r] < left)
+                reinterpret_cast<uint32_t *>(obase + off[r])[t] =
+                    az_pack_bf16x2(fmaxf(acc[2 * r] + bias0, 0.f), fmaxf(acc[2 * r + 1] + bias1, 0.f));
     }
 }

@@ -285,8 +285,10 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
 def test_evaluator_glue_kernels_slab_layout(n, N):
     """The slab-layout stem and heads (k_nn_stem_slab / k_nn_heads_slab, the
     two ends of the tcgen05 tower) against the plain-layout kernels on the
-    same inputs.  Summation order differs, so outputs may differ by one bf16
-    rounding (rel 2^-7 + abs 1e-3); everything that is not a board cell stays
+    same inputs.  Summation order differs (and the slab stem pre-adds the
+    three taps of a kernel row into one bf16 table entry), so outputs may
+    differ by a bf16 rounding or two (rel 2^-6 + abs 1e-2 for the stem, rel
+    2^-7 + abs 1e-3 for the heads); everything that is not a board cell stays
     zero."""
     import ctypes
     from azalea_b200 import _cabi, tower_layout as tl
@@ -310,7 +312,7 @@ def test_evaluator_glue_kernels_slab_layout(n, N):
     got, rest = tl.from_slabs(slab, n, N)
     bpg = tl.boards_per_group(n)
     assert rest == 0.0
-    assert ((got.float() - plain.float()).abs() <= plain.float().abs() * 2 ** -7 + 1e-3).all()
+    assert ((got.float() - plain.float()).abs() <= plain.float().abs() * 2 ** -6 + 1e-2).all()
     # unused board slots of the last group are never written by the stem
     full = tl.from_slabs(slab, n, (N + bpg - 1) // bpg * bpg)[0]
     assert float(full[N:].float().abs().sum()) == 0.0

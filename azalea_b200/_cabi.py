@@ -103,7 +103,7 @@ def lib():
                                     f32p, f32p, vp, vp, i32p, vp]
     L.az_nn_stem.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, f32p, vp, C.c_int,
                              C.c_int, vp]
-    L.az_nn_heads.argtypes = [vp, C.c_int64, f32p, f32p, vp, C.c_int, C.c_int, C.c_int, vp]
+    L.az_nn_heads.argtypes = [vp, C.c_int64, f32p, f32p, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
     L.az_nn_tower_group.argtypes = [C.c_int]
     L.az_nn_tower_halo.argtypes = [C.c_int]
     L.az_nn_tower_rows.argtypes = [C.c_int, C.c_int64]

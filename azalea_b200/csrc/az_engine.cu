@@ -969,8 +969,10 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
 }
 
 int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const float *b_dev,
-                void *out_dev, int channels, int heads, int padded_board_size, void *stream)
+                void *out_dev, int64_t out_board_stride, int channels, int heads, int padded_board_size,
+                void *stream)
 {
+    if (out_board_stride && !padded_board_size) return AZ_E_UNSUPPORTED;
     if (padded_board_size && channels != 64) return AZ_E_UNSUPPORTED;
     if (!x_dev || !w_dev || !b_dev || !out_dev || channels < 8 || channels > AZ_NN_MAXC ||
         (channels & 7) || positions < 0)
@@ -982,11 +984,13 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
     if (padded_board_size) {
         const int n = padded_board_size, bpg = 128 / (n + 1);
         if (n < 2 || n > 19 || positions % (n * n)) return AZ_E_INVALID;
+        if (out_board_stride == 0) out_board_stride = (int64_t)n * n * heads;
+        if (out_board_stride < n * n * heads || (out_board_stride & 1)) return AZ_E_INVALID;
         const long long boards = positions / (n * n);
         long long blocks = (boards + bpg - 1) / bpg * n;
         if (blocks > 148 * 8) blocks = 148 * 8;
         k_nn_heads_slab<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            (const uint16_t *)x_dev, boards, n, w_dev, b_dev, (uint16_t *)out_dev);
+            (const uint16_t *)x_dev, boards, n, w_dev, b_dev, (uint16_t *)out_dev, (long long)out_board_stride);
         return az_check(cudaGetLastError());
     }
     long long blocks = (positions * (channels >> 3) + 255) / 256;

@@ -296,11 +296,11 @@ __device__ __forceinline__ void az_mma_bf16_16816(float (&c)[4], const uint32_t 
 template <int H>
 __global__ void __launch_bounds__(256)
 k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float *__restrict__ w,
-                const float *__restrict__ b, uint16_t *__restrict__ out)
+                const float *__restrict__ b, uint16_t *__restrict__ out, long long ostride)
 {
     static_assert(H <= 8 && (H & 1) == 0, "heads fit one n = 8 MMA tile");
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int nn = n * n, pn1 = n + 1, bpg = 128 / pn1;
+    const int pn1 = n + 1, bpg = 128 / pn1;
     // B fragments of column (head) g for the four k steps: step s covers channels
     // chunk * 8 + (s & 1) * 4 + {0..3} of chunk = t (s < 2) or t + 4
     uint32_t bhi[4][2], blo[4][2];
@@ -318,14 +318,16 @@ k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float 
         }
     const float bias0 = 2 * t < H ? b[2 * t] : 0.f, bias1 = 2 * t < H ? b[2 * t + 1] : 0.f;
     // this thread's two rows of every slab (l & 7 == g for both: same swizzle)
-    int lrow[2], off[2];
+    int lrow[2], bl[2];
+    long long off[2];
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         lrow[r] = (tid >> 5) * 16 + g + 8 * r;
-        const int bl = lrow[r] / pn1, bx = lrow[r] - bl * pn1;
-        off[r] = (bl * nn + bx) * H;
-        if (bl >= bpg || bx >= n) off[r] = -1;                           // pad cell
-        else if (2 * t >= H) off[r] = -1;                                // columns H..7 are padding
+        bl[r] = lrow[r] / pn1;
+        const int bx = lrow[r] - bl[r] * pn1;
+        off[r] = bl[r] * ostride + bx * H;
+        if (bl[r] >= bpg || bx >= n) bl[r] = 1 << 30;                    // pad cell
+        else if (2 * t >= H) bl[r] = 1 << 30;                            // columns H..7 are padding
     }
     const int c0 = t ^ g, c1 = (t + 4) ^ g;                              // physical chunks of logical t, t + 4
     const long long slabs = (N + bpg - 1) / bpg * n;
@@ -344,11 +346,11 @@ k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float 
             az_mma_bf16_16816(acc, f2, bhi[2]); az_mma_bf16_16816(acc, f2, blo[2]);
             az_mma_bf16_16816(acc, f3, bhi[3]); az_mma_bf16_16816(acc, f3, blo[3]);
         }
-        uint16_t *obase = out + (grp * bpg * nn + (long long)y * n) * H;
-        const long long left = (N - grp * bpg) * (long long)nn * H;     // elements of boards that exist
+        uint16_t *obase = out + grp * bpg * ostride + (long long)y * n * H;
+        const long long left = N - grp * bpg;                            // boards of this group that exist
 #pragma unroll
         for (int r = 0; r < 2; r++)
-            if (off[r] >= 0 && off[r] < left)
+            if (bl[r] < left)
                 reinterpret_cast<uint32_t *>(obase + off[r])[t] =
                     az_pack_bf16x2(fmaxf(acc[2 * r] + bias0, 0.f), fmaxf(acc[2 * r + 1] + bias1, 0.f));
     }

@@ -212,6 +212,13 @@ class HexNetwork(nn.Module):
             wm.view(-1, npc, hw).permute(0, 2, 1)
         fast['fc'] = (keep(merged),
                       keep(torch.cat([self.value_fc2.bias, self.move_fc.bias])))
+        # K and N padded to multiples of 8 with zeros for the tcgen05 path
+        kp, npd = (merged.shape[1] + 7) // 8 * 8, (merged.shape[0] + 7) // 8 * 8
+        wpad = torch.zeros(npd, kp, dtype=merged.dtype, device=merged.device)
+        wpad[:merged.shape[0], :merged.shape[1]] = merged
+        bpad = torch.zeros(npd, dtype=merged.dtype, device=merged.device)
+        bpad[:merged.shape[0]] = torch.cat([self.value_fc2.bias, self.move_fc.bias])
+        fast['fc_pad'] = (keep(wpad), keep(bpad))
         fast['nfc2'] = w2.shape[0]
         fast['value_fc3'] = (keep(self.value_fc3.weight), keep(self.value_fc3.bias))
         self._fast = fast
@@ -266,7 +273,7 @@ class HexNetwork(nn.Module):
                     ctypes.c_void_p(xh.data_ptr()), N * n * n,
                     ctypes.c_void_p(f['heads_w32'].data_ptr()),
                     ctypes.c_void_p(f['heads_b32'].data_ptr()),
-                    ctypes.c_void_p(flat.data_ptr()), C_, 6, 0, stream))
+                    ctypes.c_void_p(flat.data_ptr()), 0, C_, 6, 0, stream))
                 h = None
             else:
                 h = torch.cudnn_convolution_relu(x, *f['heads'], one, nopad, one, 1)
@@ -303,9 +310,10 @@ class HexNetwork(nn.Module):
         if bufs is None:
             # halos and pad cells must be zero; the kernels keep them zero
             bufs = (torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
-                    torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev))
+                    torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
+                    torch.zeros(N, f['fc_pad'][0].shape[1], dtype=torch.bfloat16, device=dev))
             f['tower_buf'][(npad, dev)] = bufs
-        x, y = bufs
+        x, y, flat = bufs
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
@@ -313,10 +321,13 @@ class HexNetwork(nn.Module):
         for (w1, b1), (w2, b2) in f['tower']:
             _cabi.check(L.az_nn_conv3x3(p(x), p(w1), p(b1), None, p(y), n, npad, stream))
             _cabi.check(L.az_nn_conv3x3(p(y), p(w2), p(b2), p(x), p(x), n, npad, stream))
-        flat = torch.empty(N, n * n * 6, dtype=torch.bfloat16, device=dev)
+        # head activations with the board row padded to a multiple of 8 (zeros):
+        # the merged FC GEMM then runs a current cuBLAS kernel (K = 726 falls
+        # back to a legacy one, 0.15 ms instead of 0.03)
+        wfc, bfc = f['fc_pad']
         _cabi.check(L.az_nn_heads(p(x), N * n * n, p(f['heads_w32']), p(f['heads_b32']),
-                                  p(flat), 64, 6, n, stream))
-        yfc = F.linear(flat, *f['fc'])
+                                  p(flat), flat.shape[1], 64, 6, n, stream))
+        yfc = F.linear(flat, wfc, bfc)
         k2 = f['nfc2']
         value = torch.tanh(F.linear(F.relu(yfc[:, :k2]), *f['value_fc3'])).squeeze(1)
-        return value.float(), yfc[:, k2:].float()
+        return value.float(), yfc[:, k2:k2 + n * n].float()

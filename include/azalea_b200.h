@@ -239,10 +239,13 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size,
                void *out_dev, int channels, int padded_layout, void *stream);
 /* Both 1x1 head convolutions + BN + ReLU (network.py:75-76,82-83) in one
  * pass: x bf16 [positions][channels] (NHWC), w f32 [heads][channels], b f32
- * [heads] -> out bf16 [positions][heads]; heads = 6 (2 value + 4 policy). */
+ * [heads] -> out bf16 [positions][heads]; heads = 6 (2 value + 4 policy).
+ * out_board_stride (slab layout only, else 0): elements between the rows of
+ * two consecutive boards in out, >= n*n*heads and even (0 = dense) -- lets the
+ * caller pad the row to a GEMM-friendly K; the padding is not written. */
 int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev,
-                const float *b_dev, void *out_dev, int channels, int heads,
-                int padded_board_size, void *stream);
+                const float *b_dev, void *out_dev, int64_t out_board_stride,
+                int channels, int heads, int padded_board_size, void *stream);
 
 /* One tower convolution (Resblock.conv1/conv2 + BatchNorm + ReLU, with the
  * residual add for conv2; network.py:17-39) as a tcgen05 implicit GEMM, 64 ->

@@ -265,7 +265,7 @@ def test_evaluator_glue_kernels_match_torch(n, chans):
     _cabi.check(L.az_nn_heads(ctypes.c_void_p(xin.data_ptr()), N * nn,
                               ctypes.c_void_p(f['heads_w32'].data_ptr()),
                               ctypes.c_void_p(f['heads_b32'].data_ptr()),
-                              ctypes.c_void_p(hout.data_ptr()), chans, 6, 0, stream))
+                              ctypes.c_void_p(hout.data_ptr()), 0, chans, 6, 0, stream))
     want = F.relu(xin.float() @ f['heads_w32'].t() + f['heads_b32'])
     got = hout.float()
     assert ((got - want).abs() <= want.abs() * 2 ** -7 + 1e-3).all()
@@ -320,12 +320,20 @@ def test_evaluator_glue_kernels_slab_layout(n, N):
     x = (torch.randn(N, n, n, 64, device='cuda') * 0.7).to(torch.bfloat16)
     h_plain = torch.empty(N * nn, 6, dtype=torch.bfloat16, device='cuda')
     h_slab = torch.full((N * nn + 7, 6), 7.0, dtype=torch.bfloat16, device='cuda')
-    _cabi.check(L.az_nn_heads(p(x), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_plain), 64, 6, 0, stream))
-    _cabi.check(L.az_nn_heads(p(tl.to_slabs(x)), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_slab),
-                              64, 6, n, stream))
+    _cabi.check(L.az_nn_heads(p(x), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_plain), 0, 64, 6, 0, stream))
+    xs = tl.to_slabs(x)
+    _cabi.check(L.az_nn_heads(p(xs), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_slab),
+                              0, 64, 6, n, stream))
     assert (h_slab[N * nn:] == 7.0).all()           # nothing written past the last board
     a, b = h_slab[:N * nn].float(), h_plain.float()
     assert ((a - b).abs() <= b.abs() * 2 ** -7 + 1e-3).all()
+    # padded board rows (a GEMM-friendly K): the padding is left alone
+    stride = (nn * 6 + 7) // 8 * 8 + 8
+    h_pad = torch.full((N + 1, stride), 7.0, dtype=torch.bfloat16, device='cuda')
+    _cabi.check(L.az_nn_heads(p(xs), N * nn, p(f['heads_w32']), p(f['heads_b32']), p(h_pad),
+                              stride, 64, 6, n, stream))
+    assert torch.equal(h_pad[:N, :nn * 6].reshape(N * nn, 6), h_slab[:N * nn])
+    assert (h_pad[:N, nn * 6:] == 7.0).all() and (h_pad[N] == 7.0).all()
 
 
 def test_device_replay_buffer_collate_matches_host_format():

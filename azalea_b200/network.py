@@ -318,9 +318,21 @@ class HexNetwork(nn.Module):
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
                                  p(f['stem_bias']), p(x), 64, 1, stream))
+        ev = getattr(self, 'conv_events', None)     # bench.py: per-launch CUDA events
+        cur = torch.cuda.current_stream(dev)
+
+        def conv(src, w, b, res, dst):
+            if ev is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(cur)
+            _cabi.check(L.az_nn_conv3x3(p(src), p(w), p(b), p(res) if res is not None else None,
+                                        p(dst), n, npad, stream))
+            if ev is not None:
+                e1.record(cur)
+                ev.append((e0, e1, res is not None, N))
         for (w1, b1), (w2, b2) in f['tower']:
-            _cabi.check(L.az_nn_conv3x3(p(x), p(w1), p(b1), None, p(y), n, npad, stream))
-            _cabi.check(L.az_nn_conv3x3(p(y), p(w2), p(b2), p(x), p(x), n, npad, stream))
+            conv(x, w1, b1, None, y)
+            conv(y, w2, b2, x, x)
         # head activations with the board row padded to a multiple of 8 (zeros):
         # the merged FC GEMM then runs a current cuBLAS kernel (K = 726 falls
         # back to a legacy one, 0.15 ms instead of 0.03)

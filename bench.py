@@ -368,6 +368,9 @@ def run_ours(args):
     sel_ev, exp_ev = [], []
     cs0 = sp.counters()
     sel_ms = exp_ms = 0.0
+    conv_ev = None
+    if args.evaluator == 'net' and getattr(evaluator, 'tower', None) == 'tcgen05':
+        conv_ev = evaluator.conv_events = []
     eng.select_root()
     sp._evaluate(True)
     eng.expand_root(None, 1 if args.evaluator == 'net' else 0)
@@ -384,6 +387,8 @@ def run_ours(args):
         exp_ev.append((c, d))
     eng.play_commit(sp.temperature, sp.depth, sp.move_sampling, True, True, sp.chosen)
     torch.cuda.synchronize()
+    if conv_ev is not None:
+        evaluator.conv_events = None
     sel_ms = sum(a.elapsed_time(b) for a, b in sel_ev)
     exp_ms = sum(a.elapsed_time(b) for a, b in exp_ev)
     cs1 = sp.counters()
@@ -412,6 +417,39 @@ def run_ours(args):
         'expand_backup_avg_launch_ms': exp_ms / launches,
         'note': 'latency/occupancy-bound pointer chasing; see DESIGN.md',
     }
+    roofline_tree = None
+    if conv_ev:
+        # the dominant kernel of the step with the network evaluator: k_conv3x3
+        # (csrc/az_tower.cuh).  Algorithmic bytes per board and launch:
+        # n*n cells x 64 channels x 2 B read + as much written, + as much again
+        # for the residual of the second convolution of a block.
+        cell_bytes = args.board * args.board * 128
+        cbytes = sum(boards * cell_bytes * (3 if res else 2) for _, _, res, boards in conv_ev)
+        cflop = sum(boards * args.board * args.board * 2 * 64 * 576 for _, _, _, boards in conv_ev)
+        cms = sum(a.elapsed_time(b) for a, b, _, _ in conv_ev)
+        conv_traffic = None
+        try:
+            conv_traffic = tj['k_conv3x3'][f'{args.board}x{args.board}/{G * sp.batch}']['traffic_bytes']
+        except Exception:
+            pass
+        roofline_tree = roofline
+        achieved_c = cbytes / (cms * 1e-3) / 1e9
+        roofline = {
+            'kernel': 'k_conv3x3', 'bound': 'hbm', 'achieved': achieved_c,
+            'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved_c / hbm_peak,
+            'traffic': conv_traffic, 'peak_source': peak_src,
+            'launches_timed': len(conv_ev), 'avg_launch_ms': cms / len(conv_ev),
+            'alg_bytes_per_launch': cbytes / len(conv_ev),
+            'avg_launch_ms_plain': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if not r)
+                                    / max(1, sum(1 for e in conv_ev if not e[2]))),
+            'avg_launch_ms_residual': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if r)
+                                       / max(1, sum(1 for e in conv_ev if e[2]))),
+            'useful_tflops': cflop / (cms * 1e-3) / 1e12,
+            'tensor_peak_tflops_sustained': float(peaks.get('bf16_tflops_sustained', 1400.0)),
+            'conv_share_of_step': cms / (ms / args.steps),
+            'note': 'two launches per residual block: x->y (2 units of traffic) and y,x->x (3 units); '
+                    'the second sits on the HBM roofline, the first between HBM and the tensor pipe',
+        }
     nn_info = None
     if args.evaluator == 'net':
         step_ms = ms / args.steps
@@ -488,8 +526,9 @@ def run_ours(args):
                     'd2h_bytes_per_step': d2h // max(1, args.steps),
                     'ms_per_step': 1e3 * e2e_s / args.steps,
                     'replay_rows_per_step': rows_out / args.steps},
-            'gpu_launches': args.steps * sp_launches(args, per_move),
+            'gpu_launches': args.steps * sp_launches(args, per_move, evaluator),
             'roofline': roofline,
+            'roofline_tree': roofline_tree,
             'cpu_baseline': cpu_baseline,
             'tree_only': tree_only,
             'network': nn_info,
@@ -501,13 +540,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def sp_launches(args, per_move):
+def sp_launches(args, per_move, evaluator=None):
     """Kernels of ours per step: select_root, expand_root, commit, and per
-    search batch select + expand_backup (+ the stub evaluator kernels)."""
+    search batch select + expand_backup, plus per evaluation (root + every
+    search batch) the stub kernel, or the network's stem + heads kernels and,
+    with the tcgen05 tower, two k_conv3x3 per residual block."""
     nb = per_move // SEARCH['search_batch_size']
     per = 3 + 2 * nb
     if args.evaluator == 'stub':
         per += nb + 1
+    else:
+        own = 2
+        if getattr(evaluator, 'tower', None) == 'tcgen05':
+            own += 2 * len(evaluator.resblocks)
+        per += (nb + 1) * own
     return per
 
 

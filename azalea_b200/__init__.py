@@ -14,6 +14,7 @@ from .game.hex import HexGame
 from .parallel_player import Player
 from .play_game import play_game
 from .policy import Policy
+from . import policy_trainer
 from .random_policy import RandomPolicy
 from .replay_buffer import ReplayDataFrame, ReplayRecord
 from .replay_device import DeviceReplayBuffer
@@ -25,4 +26,4 @@ __all__ = ['AzaleaAgent', 'Engine', 'HexGame', 'Player', 'play_game',
            'Policy', 'RandomPolicy', 'ReplayDataFrame', 'ReplayRecord',
            'SearchTree', 'SearchTreeFull', 'as_distribution',
            'LockstepSelfPlay', 'StubEvaluator', 'DeviceReplayBuffer', 'evaluate',
-           'play_matches', 'typing', 'utils']
+           'play_matches', 'policy_trainer', 'typing', 'utils']

@@ -274,6 +274,28 @@ __global__ void k_root_stats(az_engine e, float *visits, float *total_value, flo
     }
 }
 
+// RandomPolicy.choose_action (random_policy.py:25-41) in terms of the tree: one
+// visit on every child of the (expanded) root, so that az_play_commit with
+// temperature 1 draws the move uniformly and records moves_prob = 1 / k.
+__global__ void k_root_uniform(az_engine e)
+{
+    const int lane = az_lane();
+    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.G) return;
+    const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
+    if (meta[M_STATUS] != 0) return;
+    uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
+    const uint4 root = nodes[0];
+    if (root.w == AZ_UNEVAL) return;
+    const int k = (int)(root.w & AZ_LINK_KMASK), fc = (int)(root.w >> AZ_LINK_KBITS);
+    for (int j = lane; j < k; j += 32) {
+        uint4 r = nodes[fc + j];
+        r.x = __float_as_uint(1.0f);
+        r.y = 0u;
+        nodes[fc + j] = r;
+    }
+}
+
 __global__ void k_tree_move(az_engine e, const int32_t *move_ids)
 {
     const int lane = az_lane();
@@ -883,6 +905,12 @@ int az_root_stats(az_engine *e, float *visits_dev, float *total_value_dev, float
     if (!e) return AZ_E_INVALID;
     AZ_LAUNCH(k_root_stats, e, stream, visits_dev, total_value_dev, prior_dev, num_children_dev,
               root_nw_dev, num_nodes_dev);
+}
+
+int az_mcts_root_uniform(az_engine *e, void *stream)
+{
+    if (!e) return AZ_E_INVALID;
+    AZ_LAUNCH(k_root_uniform, e, stream);
 }
 
 int az_tree_move(az_engine *e, const int32_t *move_ids_dev, void *stream)

@@ -184,6 +184,11 @@ class Engine:
                                      _ptr(num_nodes), self._stream))
         return visits, total, prior, k, root_nw, num_nodes
 
+    def root_uniform(self):
+        """One visit on every child of every expanded root: the RandomPolicy
+        seat (random_policy.py:25-41) in terms of the tree."""
+        check(self.lib.az_mcts_root_uniform(self._h, self._stream))
+
     def tree_move(self, move_ids):
         """SearchTree.move (search_tree.py:115-132); -1 = skip."""
         move_ids = torch.as_tensor(move_ids, dtype=torch.int32).to(

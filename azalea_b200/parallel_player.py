@@ -12,6 +12,7 @@ from typing import Dict, Sequence, Tuple
 import numpy as np
 
 from .engine import decode_replay_rows
+from .random_policy import RandomPolicy
 from .replay_buffer import ReplayDataFrame
 from .selfplay import LockstepSelfPlay, rows_to_dataframe
 
@@ -26,6 +27,12 @@ class Player:
         board_size = agents[0].game.board_size
         settings = policy.settings
         self.board_size = board_size
+        if isinstance(policy, RandomPolicy):
+            # AzaleaAgent(game_factory) without a policy: random self-play
+            self.sp = LockstepSelfPlay(None, num_games=num_games, board_size=board_size,
+                                       random_play=True, seed=seed, **kwargs)
+            self.running = True
+            return
         self.sp = LockstepSelfPlay(
             policy.net, num_games=num_games, board_size=board_size,
             simulations=policy.simulations,
@@ -79,4 +86,5 @@ class Player:
         return torch.cat(chunks), metrics
 
     def stop(self) -> None:
+        """parallel_player.py:49-52; nothing to shut down here."""
         self.running = False

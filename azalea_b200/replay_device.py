@@ -61,6 +61,20 @@ class DeviceReplayBuffer:
         self.put(rows)
         return metrics
 
+    def state_dict(self) -> Dict:
+        """replay_buffer.py:151-158, with the rows as one uint8 tensor."""
+        return {'rows': self.rows[:self.size].cpu(), 'board_size': self.n,
+                'capacity': self.capacity, 'write_idx': self.write_idx,
+                'fresh_counter': self.fresh_counter}
+
+    def load_state_dict(self, state: Dict) -> None:
+        assert state['board_size'] == self.n and state['capacity'] == self.capacity
+        rows = state['rows']
+        self.rows[:rows.shape[0]] = rows.to(self.device)
+        self.size = rows.shape[0]
+        self.write_idx = state['write_idx']
+        self.fresh_counter = state['fresh_counter']
+
     def sample(self, batch_size: int, generator: Optional[torch.Generator] = None,
                trim: bool = True) -> Dict[str, torch.Tensor]:
         """A uniformly sampled minibatch as the reference's collated dict:

@@ -45,7 +45,16 @@ class LockstepSelfPlay:
                  move_sampling=True, move_exploration=True, seed=0,
                  device=None, rank=0, world_size=1, nodes_per_game=None,
                  replay_rows=None, collect_replay=True, cuda_graph=True,
-                 max_plies=300):
+                 max_plies=300, random_play=False):
+        # random_play: RandomPolicy self-play (random_policy.py:25-41) -- no
+        # search, uniform move choice and uniform moves_prob at every ply;
+        # how the reference fills the replay buffer before training
+        # (policy_trainer.py:145-158)
+        self.random_play = bool(random_play)
+        if self.random_play:
+            evaluator = StubEvaluator(0)
+            simulations, exploration_depth = 0, 1 << 30
+            exploration_temperature, move_sampling = 1.0, True
         self.evaluator = evaluator
         self.G = int(num_games)
         self.n = int(board_size)
@@ -109,7 +118,9 @@ class LockstepSelfPlay:
         eng.select_root()
         _, _, kind = self._evaluate(True)
         eng.expand_root(None, kind)
-        for _ in range(self.num_batches):
+        if self.random_play:
+            eng.root_uniform()
+        for _ in range(0 if self.random_play else self.num_batches):
             eng.select(self.batch, self.coef, self.noise_scale,
                        self.noise_alpha)
             value, prior, kind = self._evaluate(False)

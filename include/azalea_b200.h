@@ -200,6 +200,14 @@ int az_mcts_expand_root(az_engine *e, const float *prior_dev, int prior_kind,
 int az_root_stats(az_engine *e, float *visits_dev, float *total_value_dev,
                   float *prior_dev, int32_t *num_children_dev,
                   float *root_nw_dev, int64_t *num_nodes_dev, void *stream);
+/* RandomPolicy.choose_action (random_policy.py:25-41) for every game: puts
+ * one visit on each child of the expanded root (az_mcts_select_root +
+ * evaluator + az_mcts_expand_root first), so that az_play_commit with
+ * temperature 1 and sampling draws the move uniformly and the replay row
+ * records moves_prob = 1 / num_moves.  Used to fill the replay buffer before
+ * training (policy_trainer.py:145-158). */
+int az_mcts_root_uniform(az_engine *e, void *stream);
+
 /* SearchTree.move, search_tree.py:115-132: re-root to child move_id (with
  * subtree compaction) or reset when it is unevaluated; move_id -1 = skip. */
 int az_tree_move(az_engine *e, const int32_t *move_ids_dev, void *stream);

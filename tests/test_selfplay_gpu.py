@@ -456,3 +456,81 @@ def test_tcgen05_tower_matches_cudnn_tower():
     assert (v0 - v1).abs().max() < 0.03
     lp0, lp1 = torch.log_softmax(l0, 1), torch.log_softmax(l1, 1)
     assert (lp0 - lp1).abs().max() < 0.15 and (lp0 - lp1).abs().mean() < 0.01
+
+
+def test_random_policy_selfplay_rows():
+    """Player over an AzaleaAgent without a policy (RandomPolicy,
+    random_policy.py:25-41): uniform moves_prob = 1 / num_moves at every ply,
+    whole games with rewards; the way the reference fills the replay buffer
+    before training (policy_trainer.py:145-158)."""
+    import azalea_b200 as az
+    agent = az.AzaleaAgent(lambda: az.HexGame(5))
+    player = az.Player(None, [agent], num_games=64, seed=3)
+    df, metrics = player.read(300)
+    assert len(df) >= 300 and metrics['games'] > 0 and metrics['game_error'] == 0
+    first_moves = set()
+    for state, probs, reward in zip(df.state, df.moves_prob, df.reward):
+        k = len(state.legal_moves)
+        assert probs.shape == (k,) and np.allclose(probs, 1.0 / k)
+        assert reward in (-1.0, 1.0)
+        if k == 25:
+            first_moves.add(int(np.count_nonzero(state.board)))
+    assert first_moves == {0}
+    # moves are spread: many distinct second-ply boards among the games
+    second = {s.board.tobytes() for s in df.state if len(s.legal_moves) == 24}
+    assert len(second) >= 15
+
+
+def test_policy_trainer_closes_the_loop(tmp_path):
+    """policy_trainer.train (policy_trainer.py:24-120) with GPU self-play:
+    random-policy buffer fill, SGD steps on device-collated minibatches,
+    replay refills by the policy under training (weights refreshed in place),
+    checkpoint in the reference's format."""
+    import azalea_b200 as az
+    from azalea_b200 import policy_trainer
+    config = dict(seed=0xBAD5EED5, device='cuda', game='hex', network='HexNetwork', board_size=5,
+                  num_blocks=1, base_chans=64, simulations=20, search_batch_size=5,
+                  exploration_coef=0.5, exploration_temperature=1.0, exploration_depth=15,
+                  exploration_noise_alpha=0.03, exploration_noise_scale=0.25,
+                  replaybuf_size=2048, replaybuf_resample=2, batch_size=128, lr_initial=0.05,
+                  lr_decay_steps=4, lr_decay=0.5, momentum=0.9, l2_regularization=1e-4,
+                  total_steps=8, log_interval=4, model_checkpoint_interval=0,
+                  num_selfplay_games=64)
+    policy = az.Policy()
+    policy.initialize(config)
+    before = [p.detach().clone() for p in policy.net.parameters()]
+    path = policy_trainer.train(policy, config, str(tmp_path))
+    hist = policy_trainer.train.history
+    assert len(hist) == 8 and all(np.isfinite(h['loss']) for h in hist)
+    assert hist[0]['lr'] == 0.05 and hist[-1]['lr'] == pytest.approx(0.05 * 0.25)
+    # 128 / 2 = 64 consumed per step against 2048 fresh random rows: refills by the network
+    # start once those are used up -- force one more refill to see self-play with the trained net
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, policy.net.parameters()))
+    loaded = az.Policy.load(path, device='cuda')
+    assert loaded.simulations == 20 and loaded.board_size == 5
+    for a, b in zip(loaded.net.parameters(), policy.net.parameters()):
+        assert torch.equal(a.cpu(), b.detach().cpu())
+    # the loss on uniform-random data starts near log(moves) + value variance
+    assert 1.0 < hist[0]['loss'] < 6.0
+
+
+def test_policy_trainer_refills_from_network_selfplay(tmp_path):
+    """With a small buffer the fresh rows run out and the trainer refills from
+    self-play by the current network (replay_buffer.py:121-132)."""
+    import azalea_b200 as az
+    from azalea_b200 import policy_trainer
+    config = dict(seed=7, device='cuda', game='hex', network='HexNetwork', board_size=5,
+                  num_blocks=1, base_chans=64, simulations=10, search_batch_size=5,
+                  exploration_coef=0.5, exploration_temperature=1.0, exploration_depth=15,
+                  exploration_noise_alpha=0.03, exploration_noise_scale=0.25,
+                  replaybuf_size=256, replaybuf_oversampling=1, batch_size=128, lr_initial=0.01,
+                  lr_decay_epochs=100, lr_decay=0.5, momentum=0.9, l2_regularization=1e-4,
+                  total_epochs=3, log_interval=0, model_checkpoint_interval=0,
+                  num_selfplay_games=32)
+    policy = az.Policy()
+    policy.initialize(config)
+    policy_trainer.train(policy, config, str(tmp_path))
+    hist = policy_trainer.train.history
+    assert len(hist) == 6                       # 3 epochs x (256 // 128) steps
+    assert sum(h.get('selfplay_games', 0) for h in hist) > 0
+    assert not policy.net.training

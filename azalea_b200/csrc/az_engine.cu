@@ -1060,7 +1060,9 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, c
     p.resid = (const uint8_t *)resid_dev; p.out = (uint8_t *)out_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
-    { const char *dbg = getenv("AZT_DEBUG"); p.debug = dbg ? atoi(dbg) : 0; }
+    static int debug = -1;                  /* probe switches (az_tower.cuh), read once */
+    if (debug < 0) { const char *dbg = getenv("AZT_DEBUG"); debug = dbg ? atoi(dbg) : 0; }
+    p.debug = debug;
     static int sm_count = 0;
     static bool attr_set = false;
     if (!attr_set) {

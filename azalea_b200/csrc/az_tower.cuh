@@ -327,13 +327,18 @@ k_conv3x3(const azt_params p)
                             for (int k = 0; k < 4; k++)
                                 azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
                     } else {
+                        // one accumulator range after the other: alternating between two
+                        // costs ~33 cycles per switch (tools/probe/umma_gap.cu)
 #pragma unroll
                         for (int dx = 0; dx < 3; dx++)
 #pragma unroll
-                            for (int k = 0; k < 4; k++) {
+                            for (int k = 0; k < 4; k++)
                                 azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++)
                                 azt_mma(tmem, da0 + (dx * 8 + k * 2), db1 + (dx * 192 * 8 + k * 2), i1);
-                            }
                     }
                 }
                 // one commit per slab: output slabs wait for it, and so does the input stage

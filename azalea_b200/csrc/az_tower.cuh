@@ -62,6 +62,7 @@
 //   warp 18     one thread streams input slabs through a 4-stage ring
 //   warp 19     one thread bulk-loads residual slabs into the staging tiles
 //   warp 20     one thread bulk-stores finished staging tiles
+//   (HEADS variant, last layer: warps 20-27 project the finished tiles onto the heads instead)
 #pragma once
 
 #include <cuda_bf16.h>
@@ -79,7 +80,8 @@
 #define AZT_OUT_BYTES (128 * AZT_ROW)
 #define AZT_OUT_STAGES 5            // staging slabs: residual in, finished slab out
 #define AZT_SMEM_BYTES (AZT_WBYTES + AZT_STAGES * AZT_CHUNK_BYTES + AZT_OUT_STAGES * AZT_OUT_BYTES)
-#define AZT_THREADS 672
+#define AZT_THREADS 672            // 768 for the HEADS variant (four head warps instead of the storer)
+#define AZT_THREADS_HEADS 896
 #define AZT_BLOCKS 8                // TMEM ring: 8 x 64 columns
 
 struct azt_params {
@@ -88,6 +90,11 @@ struct azt_params {
     const float *bias;      // [64]
     const uint8_t *resid;   // residual input (same layout) or NULL
     uint8_t *out;           // output activations
+    // HEADS variant (last tower layer): the 64 -> 6 head projection + ReLU of the finished slab
+    // goes to hout[board * hstride + tile * 6 + head] (bf16) instead of `out`
+    uint16_t *hout;
+    long long hstride;      // elements between boards in hout
+    long long boards;       // boards that exist (the last group may be partial)
     int n;                  // board size
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
@@ -182,8 +189,12 @@ __device__ __forceinline__ void azt_tmem_zero16(uint32_t addr)
         ::"r"(addr), "r"(z) : "memory");
 }
 
-template <bool RESID>
-__global__ void __launch_bounds__(AZT_THREADS, 1)
+// head weights [6][64] + bias [6] of the HEADS variant (copied device-to-device, stream-ordered,
+// by az_nn_conv3x3_heads before every launch)
+__constant__ float azt_heads_const[6 * 64 + 8];
+
+template <bool RESID, bool HEADS>
+__global__ void __launch_bounds__(AZT_THREADS_HEADS, 1)
 k_conv3x3(const azt_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -209,7 +220,8 @@ k_conv3x3(const azt_params p)
         for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
         for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
         for (int i = 0; i < AZT_OUT_STAGES; i++) {
-            azt_mbar_init(&bar_out_full[i], 1); azt_mbar_init(&bar_out_empty[i], 1);
+            azt_mbar_init(&bar_out_full[i], 1);
+            azt_mbar_init(&bar_out_empty[i], HEADS ? 4 : 1);    // released by the storer (HEADS: by the four head warps)
             azt_mbar_init(&bar_out_done[i], 8);         // one arrival per warp of the group that wrote the slab
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -243,9 +255,63 @@ k_conv3x3(const azt_params p)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    if (warp == 20) {
+    if (warp >= 20 && HEADS) {
+        // ---------------------------------------------------- head warps --
+        // Two groups of four warps (alternate slabs) project every finished slab 64 -> 6 (+ bias, ReLU) straight from its
+        // staging tile, one row per thread, on plain FMAs whose weight operands come from the
+        // constant bank (no weight loads at all).  Deliberately not mma.sync: legacy tensor
+        // instructions interleaved with the tcgen05 stream stall it (the mma.sync version of
+        // this block made the kernel 20 % slower than the unfused one).
+        const int hgrp = (warp - 20) >> 2;                         // two groups of four warps on alternate slabs
+        const int row = ((warp - 20) & 3) * 32 + lane, sw = row & 7;
+        const int bl = row / (n + 1), bx = row - bl * (n + 1);
+        const bool cell = bl < p.bpg && bx < n;                     // not a pad cell
+        const long long hoff = bl * p.hstride + bx * 6;
+        long long hgroup = g0;
+        for (int j = hgrp, y = hgrp; j < ((p.debug & 4) ? 0 : nslabs); j += 2, y += 2) {
+            if (y >= n) { y -= n; hgroup++; }
+            const int sb = j % AZT_OUT_STAGES;
+            azt_mbar_wait(&bar_out_done[sb], (j / AZT_OUT_STAGES) & 1);
+            const uint4 *srow = reinterpret_cast<const uint4 *>(s_out + sb * AZT_OUT_BYTES + row * AZT_ROW);
+            uint4 v[8];
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) v[c8] = srow[c8 ^ sw];
+            // the next writer of this tile is a bulk copy (async proxy): order our reads before it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_out_empty[sb]);            // staging slab free again
+            float acc[6][2];
+#pragma unroll
+            for (int h = 0; h < 6; h++) acc[h][0] = acc[h][1] = 0.f;
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) {
+                const uint32_t vw[4] = {v[c8].x, v[c8].y, v[c8].z, v[c8].w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float f0 = __uint_as_float(vw[q] << 16), f1 = __uint_as_float(vw[q] & 0xffff0000u);
+#pragma unroll
+                    for (int h = 0; h < 6; h++) {
+                        // weights are constant-bank operands of the FMAs: no loads
+                        acc[h][0] = fmaf(f0, azt_heads_const[h * 64 + c8 * 8 + 2 * q], acc[h][0]);
+                        acc[h][1] = fmaf(f1, azt_heads_const[h * 64 + c8 * 8 + 2 * q + 1], acc[h][1]);
+                    }
+                }
+            }
+            if (cell && hgroup * p.bpg + bl < p.boards) {
+                float o[6];
+#pragma unroll
+                for (int h = 0; h < 6; h++) o[h] = fmaxf(acc[h][0] + acc[h][1] + azt_heads_const[6 * 64 + h], 0.f);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(p.hout + hgroup * p.bpg * p.hstride + (long long)y * n * 6 + hoff);
+#pragma unroll
+                for (int h = 0; h < 3; h++) {
+                    __nv_bfloat162 hh = __floats2bfloat162_rn(o[2 * h], o[2 * h + 1]);
+                    dst[h] = *reinterpret_cast<uint32_t *>(&hh);
+                }
+            }
+        }
+    } else if (warp >= 20) {
         // -------------------------------------------------------- storer --
-        if (lane == 0 && !(p.debug & 4)) {
+        if (warp == 20 && lane == 0 && !(p.debug & 4)) {
             for (int j = 0; j < nslabs; j++) {
                 const int sb = j % AZT_OUT_STAGES;
                 azt_mbar_wait(&bar_out_done[sb], (j / AZT_OUT_STAGES) & 1);
@@ -418,7 +484,7 @@ k_conv3x3(const azt_params p)
             __syncwarp();
             if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
             if (p.debug & 4) continue;
-            // staging slab complete: the storer sends it to global memory
+            // staging slab complete: the storer sends it to global memory (HEADS: the head warps project it)
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);

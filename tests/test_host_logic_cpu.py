@@ -138,3 +138,37 @@ def test_game_sharding_is_world_size_invariant():
                 assert gid not in seen
                 seen.add(gid)
     assert seen == set(range(5 * W * G))
+
+
+def test_tower_layout_helpers_roundtrip():
+    """azalea_b200/tower_layout.py (the slab activation layout of the tcgen05
+    tower, csrc/az_tower.cuh) on CPU tensors: the row formula, the 16-byte
+    chunk swizzle, the weight packing order and the round trip."""
+    import torch
+    from azalea_b200 import tower_layout as tl
+    for n, N in ((11, 23), (19, 7), (5, 1), (7, 33)):
+        bpg = tl.boards_per_group(n)
+        assert bpg == 128 // (n + 1)
+        groups = (N + bpg - 1) // bpg
+        assert tl.buffer_rows(n, N) == 8 + groups * n * 128 + 16
+        x = torch.arange(N * n * n * 64, dtype=torch.float32).reshape(N, n, n, 64) % 251
+        buf = tl.to_slabs(x)
+        assert buf.shape == (tl.buffer_rows(n, N), 64)
+        back, rest = tl.from_slabs(buf, n, N)
+        assert torch.equal(back, x) and rest == 0.0
+        # one cell by hand: board b, row y, column c -> row R, chunk j stored at j ^ (R & 7)
+        b, y, c = N - 1, n - 1, n // 2
+        R = 8 + ((b // bpg) * n + y) * 128 + (b % bpg) * (n + 1) + c
+        for j in range(8):
+            phys = j ^ (R & 7)
+            assert torch.equal(buf[R, phys * 8:phys * 8 + 8], x[b, y, c, j * 8:j * 8 + 8])
+        # the pad cell after each board row is zero
+        assert float(buf[R - c + n].abs().sum()) == 0.0
+    w = torch.arange(64 * 64 * 9, dtype=torch.float32).reshape(64, 64, 3, 3)
+    wp = tl.pack_conv_weights(w)
+    assert wp.shape == (576, 64)
+    for kx, ky, co in ((0, 0, 0), (2, 1, 37), (1, 2, 63)):
+        row = (kx * 3 + ky) * 64 + co
+        for j in (0, 5):
+            phys = j ^ (row & 7)
+            assert torch.equal(wp[row, phys * 8:phys * 8 + 8], w[co, j * 8:j * 8 + 8, ky, kx])

@@ -192,8 +192,12 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
 // + 16 v(x+1) indexes T3[dy][code][c] = sum_dx T[dy*3+dx][v_dx][c] (bf16, 24 KB
 // of shared memory, built once per block), and the three codes of a cell are
 // one packed word, so a 16-byte output chunk is 1 LDS.32 + 3 conflict-free
-// LDS.128 + 24 FADD instead of nine byte loads and nine table lookups.
-#define AZ_STEM_SLAB_SMEM(n, bpg) (3 * 64 * 64 * 2 + (bpg) * (n) * (n) * 4 + (((bpg) * ((n) + 2) * ((n) + 2) + 15) & ~15))
+// LDS.128 + 16 FADD instead of nine byte loads and nine table lookups (the bias
+// rides on the centre row's entries, ReLU on the bf16 conversion).
+#define AZ_STEM_SLAB_ITEMS(n, bpg) ((bpg) * ((n) + 2) * ((n) + 2))
+#define AZ_STEM_SLAB_SMEM(n, bpg) \
+    (3 * 64 * 64 * 2 + (bpg) * (n) * (n) * 4 + ((AZ_STEM_SLAB_ITEMS(n, bpg) + 15) & ~15) + \
+     2 * ((AZ_STEM_SLAB_ITEMS(n, bpg) + 7) & ~7) + 2 * (((bpg) * (n) * (n) + 7) & ~7))
 
 __global__ void __launch_bounds__(256)
 k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
@@ -203,23 +207,34 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint16_t *t3 = reinterpret_cast<uint16_t *>(smem_raw);              // [3 dy][64 codes][64 c]
     uint32_t *scode = reinterpret_cast<uint32_t *>(smem_raw + 3 * 64 * 64 * 2);      // [bpg][n][n]
-    const int pn = n + 2, pn1 = n + 1, bpg = 128 / pn1;
-    int8_t *scell = reinterpret_cast<int8_t *>(scode + bpg * n * n);    // [bpg][n + 2][n + 2]
+    const int pn = n + 2, pn1 = n + 1, bpg = 128 / pn1, items = bpg * pn * pn, ncell = bpg * n * n;
+    int8_t *scell = reinterpret_cast<int8_t *>(scode + ncell);          // [bpg][n + 2][n + 2]
+    // index arithmetic of the two staging passes, done once per block:
+    // lsrc[i] = offset of padded cell i in the group's boards (0xffff: border), ltl[i] = padded
+    // index of the top-left neighbour of cell i
+    uint16_t *lsrc = reinterpret_cast<uint16_t *>(scell + ((items + 15) & ~15));
+    uint16_t *ltl = lsrc + ((items + 7) & ~7);
     const int tid = threadIdx.x;
     for (int i = tid; i < 3 * 64 * 64; i += 256) {
         const int c = i & 63, code = (i >> 6) & 63, dy = i >> 12;
-        float acc = 0.f;
+        // the centre row is always on the board: the bias rides on it
+        float acc = dy == 1 ? bias[c] : 0.f;
 #pragma unroll
         for (int dx = 0; dx < 3; dx++)
             acc += __uint_as_float((uint32_t)table[((dy * 3 + dx) * 4 + ((code >> (2 * dx)) & 3)) * 64 + c] << 16);
         t3[i] = __bfloat16_as_ushort(__float2bfloat16_rn(acc));
     }
+    for (int i = tid; i < items; i += 256) {
+        const int b = i / (pn * pn), r = (i / pn) % pn - 1, c = i % pn - 1;
+        lsrc[i] = (r >= 0 && r < n && c >= 0 && c < n) ? (uint16_t)(b * cell_stride + r * n + c) : (uint16_t)0xffff;
+    }
+    for (int i = tid; i < ncell; i += 256) {
+        const int b = i / (n * n), r = (i / n) % n, c = i % n;
+        ltl[i] = (uint16_t)((b * pn + r) * pn + c);
+    }
     // this thread's chunk of the rows l = (tid >> 3) + 32 i; the physical chunk tid & 7 holds
     // the logical chunk cg (swizzle: the row's low three bits are those of l)
     const int cg = (tid & 7) ^ ((tid >> 3) & 7);
-    float b8[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) b8[k] = bias[cg * 8 + k];
     int bl[4], co[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -227,23 +242,21 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
         bl[i] = l / pn1;
         const int bx = l - bl[i] * pn1;
         co[i] = bl[i] * n * n + bx;                                     // + y * n: this cell's code word
-        if (bl[i] >= bpg || bx >= n) bl[i] = -1;                        // pad cell: stays zero
+        if (bl[i] >= bpg || bx >= n) bl[i] = 1 << 30;                   // pad cell: stays zero
     }
     const long long groups = (N + bpg - 1) / bpg;
     for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
         __syncthreads();
         // the group's boards with a border of "off board" cells (value 3: zero table rows)
-        for (int i = tid; i < bpg * pn * pn; i += 256) {
-            const int b = i / (pn * pn), r = (i / pn) % pn - 1, c = i % pn - 1;
-            const long long board = g * bpg + b;
-            int8_t v = 3;
-            if (board < N && r >= 0 && r < n && c >= 0 && c < n) v = cells[board * cell_stride + r * n + c];
-            scell[i] = v;
+        const int8_t *gcells = cells + g * bpg * cell_stride;
+        const int limit = (int)min((long long)bpg, N - g * bpg) * cell_stride;      // boards that exist
+        for (int i = tid; i < items; i += 256) {
+            const int off = lsrc[i];
+            scell[i] = off < limit ? gcells[off] : (int8_t)3;
         }
         __syncthreads();
-        for (int i = tid; i < bpg * n * n; i += 256) {
-            const int b = i / (n * n), r = (i / n) % n, c = i % n;
-            const int8_t *sc = scell + (b * pn + r) * pn + c;           // top-left neighbour
+        for (int i = tid; i < ncell; i += 256) {
+            const int8_t *sc = scell + ltl[i];
             uint32_t word = 0;
 #pragma unroll
             for (int dy = 0; dy < 3; dy++)
@@ -251,28 +264,28 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
             scode[i] = word;
         }
         __syncthreads();
+        const int left = (int)min((long long)bpg, N - g * bpg);
         for (int y = 0; y < n; y++) {
             uint16_t *slab = out + (8 + (g * n + y) * 128) * 64;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                if (bl[i] < 0 || g * bpg + bl[i] >= N) continue;
+                if (bl[i] >= left) continue;
                 const uint32_t word = scode[co[i] + y * n];
                 float acc[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] = b8[k];
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++) {
                     const uint4 tv = *reinterpret_cast<const uint4 *>(t3 + (dy * 64 + ((word >> (8 * dy)) & 63)) * 64 + cg * 8);
                     float f[8];
                     az_bf16x8_to_f32(tv, f);
 #pragma unroll
-                    for (int k = 0; k < 8; k++) acc[k] += f[k];
+                    for (int k = 0; k < 8; k++) acc[k] = dy ? acc[k] + f[k] : f[k];
                 }
                 uint4 o;
-                o.x = az_pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-                o.y = az_pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-                o.z = az_pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-                o.w = az_pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+                // convert + ReLU in one instruction
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.x) : "f"(acc[1]), "f"(acc[0]));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.y) : "f"(acc[3]), "f"(acc[2]));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.z) : "f"(acc[5]), "f"(acc[4]));
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(o.w) : "f"(acc[7]), "f"(acc[6]));
                 reinterpret_cast<uint4 *>(slab)[tid + 256 * i] = o;
             }
         }

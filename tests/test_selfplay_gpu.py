@@ -404,7 +404,8 @@ def test_player_read_device_feeds_replay_buffer():
     assert torch.allclose(batch['moves_prob'].sum(1), torch.ones(64, device='cuda'), atol=1e-5)
 
 
-@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1), (11, 4100)))
+@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1), (11, 4100),
+                                 (2, 1), (2, 300), (3, 33), (11, 1480), (11, 1490), (13, 2000)))
 def test_tcgen05_conv3x3_matches_torch(n, N):
     """az_nn_conv3x3 (csrc/az_tower.cuh: tcgen05 implicit GEMM over the slab
     layout, N = 192 tap stacking, TMEM accumulator ring) against F.conv2d in

@@ -569,3 +569,37 @@ def test_policy_trainer_refills_from_network_selfplay(tmp_path):
     assert len(hist) == 6                       # 3 epochs x (256 // 128) steps
     assert sum(h.get('selfplay_games', 0) for h in hist) > 0
     assert not policy.net.training
+
+
+def test_tcgen05_evaluator_against_reference_network_golden():
+    """The whole bf16 evaluator on our kernels (stem, tcgen05 tower, heads)
+    against the outputs of the REFERENCE's HexNetwork on the same seeded
+    weights and boards (tests/golden/network.npz, generated by importing
+    azalea.network): value within 0.03, log-probabilities of the legal moves
+    within 0.15 (bf16 activations through 13 layers)."""
+    import os
+    from azalea_b200.network import HexNetwork
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'network.npz'))
+    torch.manual_seed(0)
+    net = HexNetwork(11, 6, 64).eval()
+    gen = torch.Generator().manual_seed(1)
+    for m in net.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=gen) * 0.1)
+            m.running_var.copy_(torch.rand(m.running_var.shape, generator=gen) + 0.5)
+            m.weight.data.copy_(torch.rand(m.weight.shape, generator=gen) + 0.5)
+            m.bias.data.copy_(torch.randn(m.bias.shape, generator=gen) * 0.1)
+    net.cuda()
+    net.prepare_inference(torch.bfloat16)
+    assert net.tower == 'tcgen05' and net._fast['tower'] is not None
+    board, moves = g['board'], g['legal_moves']
+    B = len(board)
+    cells = torch.zeros(B, 128, dtype=torch.int8, device='cuda')
+    cells[:, :121] = torch.from_numpy(board.reshape(B, 121).astype(np.int8)).cuda()
+    value, logits = net.evaluate_cells(cells)
+    assert np.abs(value.cpu().numpy() - g['value']).max() < 0.03
+    for i in range(B):
+        k = int((moves[i] > 0).sum())
+        idx = torch.from_numpy(moves[i, :k].astype(np.int64) - 1).cuda()
+        logp = torch.log_softmax(logits[i, idx], 0).cpu().numpy()
+        assert np.abs(logp - g['moves_logprob'][i, :k]).max() < 0.15, i

@@ -68,7 +68,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdio.h>
 
 #define AZT_C 64                    // channels = one 128-byte swizzle row
 #define AZT_ROW 128                 // bytes per row
@@ -99,7 +98,7 @@ struct azt_params {
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
     int debug;              // probe only: 2 = skip the output stores, 4 = skip the epilogue after the
-                            // block retirement, 8 = skip the MMAs, 16 = skip the input loads, 128 = print clocks
+                            // block retirement, 8 = skip the MMAs, 16 = skip the input loads
 };
 
 __device__ __forceinline__ uint32_t azt_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -209,11 +208,6 @@ k_conv3x3(const azt_params p)
     __shared__ __align__(16) float s_bias[AZT_C];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long dbg_c0 = 0, dbg_t0 = 0;
-    if ((p.debug & 128) && tid == 0) {
-        dbg_c0 = clock64();
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(dbg_t0));
-    }
     if (tid == 0) {
         azt_mbar_init(&bar_w, 1);
         for (int i = 0; i < AZT_STAGES; i++) azt_mbar_init(&bar_in_full[i], 1);
@@ -493,13 +487,6 @@ k_conv3x3(const azt_params p)
 #undef AZT_RING
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if ((p.debug & 128) && tid == 0 && blockIdx.x == 0) {
-        long long t1;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
-        const long long c = clock64() - dbg_c0;
-        printf("block %d: %lld cycles in %lld ns = %.3f GHz, %d slabs, %.1f cycles per slab\n", blockIdx.x, c, t1 - dbg_t0,
-               (double)c / (double)(t1 - dbg_t0), nslabs, (double)c / nslabs);
-    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
 }

@@ -98,6 +98,7 @@ def lib():
     L.az_root_stats.argtypes = [eng, f32p, f32p, f32p, i32p, f32p, vp, vp]
     L.az_tree_move.argtypes = [eng, i32p, vp]
     L.az_mcts_root_uniform.argtypes = [eng, vp]
+    L.az_engine_set_window.argtypes = [eng, C.c_int, C.c_int]
     L.az_status.argtypes = [eng, i32p, vp]
     L.az_stub_eval.argtypes = [eng, C.c_int, vp]
     L.az_replay_collate.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, i32p, i32p,

@@ -44,6 +44,7 @@ struct az_engine {
     az_config cfg;
     int device;
     int G, n, nn, NW, B, C;
+    int g0, g1;             // game window [g0, g1) the per-game kernels cover (az_engine_set_window)
     int cell_stride;        // bytes per leaf board row (nn rounded up to 16)
     int path_stride;        // uint32 per descent path
     int row_bytes;          // replay row

@@ -25,7 +25,7 @@ static int az_check(cudaError_t err)
 
 static inline int az_grid(const az_engine *e)
 {
-    return (e->G + AZ_WARPS_PER_CTA - 1) / AZ_WARPS_PER_CTA;
+    return (e->g1 - e->g0 + AZ_WARPS_PER_CTA - 1) / AZ_WARPS_PER_CTA;
 }
 
 #define AZ_LAUNCH(kernel, e, stream, ...)                                              \
@@ -67,8 +67,8 @@ __device__ __forceinline__ void az_game_reset(const az_engine &e, int g, int32_t
 __global__ void k_reset(az_engine e, const uint8_t *mask, int init)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     if (mask && !mask[g]) return;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     if (init) {
@@ -116,8 +116,8 @@ __device__ __forceinline__ int az_root_step(const az_engine &e, int g, int32_t *
 __global__ void k_hex_step(az_engine e, const int32_t *moves, int32_t *results)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     const int move = moves[g];
     int winner = meta[M_WINNER];
@@ -133,8 +133,8 @@ __global__ void k_hex_state(az_engine e, int8_t *board, int32_t *color, int32_t 
                             int32_t *ply)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     if (board) {
         const uint32_t *bx = e.board + ((size_t)g * 2 + 0) * e.NW;
@@ -155,8 +155,8 @@ __global__ void k_hex_state(az_engine e, int8_t *board, int32_t *color, int32_t 
 __global__ void k_hex_legal(az_engine e, int32_t *moves, int32_t *count)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     const uint32_t valid = az_valid_word(lane, e.nn);
     uint32_t occ = lane < e.NW
@@ -179,8 +179,8 @@ __global__ void k_hex_set_state(az_engine e, const int8_t *board, const int32_t 
                                 const int32_t *last_tile, int reset_trees)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     uint32_t x = 0, o = 0;
     for (int s = 0; s < e.NW; s++) {
@@ -221,8 +221,8 @@ __global__ void k_hex_set_state(az_engine e, const int8_t *board, const int32_t 
 __global__ void k_leaf_moves(az_engine e)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const uint32_t valid = az_valid_word(lane, e.nn);
     for (int b = 0; b < e.B; b++) {
         const int4 inf = e.leaf_info[(size_t)g * e.B + b];
@@ -250,8 +250,8 @@ __global__ void k_root_stats(az_engine e, float *visits, float *total_value, flo
                              int32_t *num_children, float *root_nw, int64_t *num_nodes)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     const uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
     const uint4 root = nodes[0];
@@ -280,8 +280,8 @@ __global__ void k_root_stats(az_engine e, float *visits, float *total_value, flo
 __global__ void k_root_uniform(az_engine e)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     if (meta[M_STATUS] != 0) return;
     uint4 *nodes = e.nodes + ((size_t)g * 2 + meta[M_HALF]) * e.C;
@@ -299,8 +299,8 @@ __global__ void k_root_uniform(az_engine e)
 __global__ void k_tree_move(az_engine e, const int32_t *move_ids)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int mv = move_ids[g];
     if (mv < 0) return;
     az_reroot(e, g, e.meta + (size_t)g * AZ_META_INTS, mv, lane);
@@ -317,8 +317,8 @@ __global__ void k_status(az_engine e, int32_t *status)
 __global__ void k_stub_eval(az_engine e, int mode)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const uint32_t valid = az_valid_word(lane, e.nn);
     for (int b = 0; b < e.B; b++) {
         const int4 inf = e.leaf_info[(size_t)g * e.B + b];
@@ -375,8 +375,8 @@ __global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32)
 k_play_commit(az_engine e, az_play_params p, int32_t *chosen)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     unsigned long long *cnt = e.counters + (size_t)g * AZ_CNT_PER_GAME;
     const int status = meta[M_STATUS];
@@ -653,6 +653,8 @@ static int az_layout(az_engine *e, const az_config *cfg)
     memset(e, 0, sizeof(*e));
     e->cfg = *cfg;
     e->G = cfg->num_games;
+    e->g0 = 0;
+    e->g1 = e->G;
     e->n = cfg->board_size;
     e->nn = e->n * e->n;
     e->NW = (e->nn + 31) / 32;
@@ -877,8 +879,9 @@ static int az_expand_launch(az_engine *e, const float *value_dev, const float *p
     az_expand_args a;
     a.batch = root_mode ? 1 : e->B;
     a.prior_kind = prior_kind;
-    a.value = value_dev ? value_dev : e->value;
-    a.prior = prior_dev ? prior_dev : e->prior;
+    /* caller arrays hold the rows of the current game window only */
+    a.value = value_dev ? value_dev - (size_t)e->g0 * e->B : e->value;
+    a.prior = prior_dev ? prior_dev - (size_t)e->g0 * e->B * e->nn : e->prior;
     a.root_mode = root_mode;
     if (e->NW <= 4) {
         AZ_LAUNCH(k_expand_backup<4>, e, stream, a);
@@ -905,6 +908,16 @@ int az_root_stats(az_engine *e, float *visits_dev, float *total_value_dev, float
     if (!e) return AZ_E_INVALID;
     AZ_LAUNCH(k_root_stats, e, stream, visits_dev, total_value_dev, prior_dev, num_children_dev,
               root_nw_dev, num_nodes_dev);
+}
+
+int az_engine_set_window(az_engine *e, int first_game, int num_games)
+{
+    if (!e) return AZ_E_INVALID;
+    if (num_games <= 0) { first_game = 0; num_games = e->G; }
+    if (first_game < 0 || first_game + num_games > e->G) return AZ_E_INVALID;
+    e->g0 = first_game;
+    e->g1 = first_game + num_games;
+    return AZ_OK;
 }
 
 int az_mcts_root_uniform(az_engine *e, void *stream)

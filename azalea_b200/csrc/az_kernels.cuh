@@ -139,8 +139,8 @@ __device__ __forceinline__ void az_dirichlet_noise(int k, float alpha, uint32_t 
 __global__ void k_noise_sample(az_engine e, float alpha, int k, int sim, float *out)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     const int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     const uint2 key = make_uint2((uint32_t)e.cfg.seed ^ (uint32_t)meta[M_GID_LO],
                                  (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
@@ -160,8 +160,8 @@ k_select(az_engine e, az_select_args a)
     __shared__ uint32_t smask_all[AZ_WARPS_PER_CTA][64];
     const int lane = az_lane();
     const int wib = threadIdx.x >> 5;
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + wib;
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + wib;
+    if (g >= e.g1) return;
     uint32_t *smask = smask_all[wib];
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     int4 *info = e.leaf_info + (size_t)g * e.B;
@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32)
 k_expand_backup(az_engine e, az_expand_args a)
 {
     const int lane = az_lane();
-    const int g = blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
-    if (g >= e.G) return;
+    const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
+    if (g >= e.g1) return;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     int status = meta[M_STATUS];
     if (status != 0) return;

@@ -184,6 +184,12 @@ class Engine:
                                      _ptr(num_nodes), self._stream))
         return visits, total, prior, k, root_nw, num_nodes
 
+    def set_window(self, first_game=0, num_games=0):
+        """Restrict the per-game kernels to games [first, first + num)
+        (0, 0: all games).  Read at launch time: see az_engine_set_window."""
+        check(self.lib.az_engine_set_window(self._h, int(first_game), int(num_games)))
+        self.window = (int(first_game), int(num_games) or self.num_games)
+
     def root_uniform(self):
         """One visit on every child of every expanded root: the RandomPolicy
         seat (random_policy.py:25-41) in terms of the tree."""

@@ -310,13 +310,16 @@ class HexNetwork(nn.Module):
         n, N, dev = self.board_size, cells.shape[0], cells.device
         npad = N
         rows = L.az_nn_tower_rows(n, N)
-        bufs = f['tower_buf'].get((npad, dev))
+        # one set of activation buffers per (batch size, stream): two halves of the games
+        # may be evaluated concurrently on two streams (selfplay.PipelinedSelfPlay)
+        stream_id = torch.cuda.current_stream(dev).cuda_stream
+        bufs = f['tower_buf'].get((npad, dev, stream_id))
         if bufs is None:
             # halos and pad cells must be zero; the kernels keep them zero
             bufs = (torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
                     torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
                     torch.zeros(N, f['fc_pad'][0].shape[1], dtype=torch.bfloat16, device=dev))
-            f['tower_buf'][(npad, dev)] = bufs
+            f['tower_buf'][(npad, dev, stream_id)] = bufs
         x, y, flat = bufs
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -45,7 +45,7 @@ class LockstepSelfPlay:
                  move_sampling=True, move_exploration=True, seed=0,
                  device=None, rank=0, world_size=1, nodes_per_game=None,
                  replay_rows=None, collect_replay=True, cuda_graph=True,
-                 max_plies=300, random_play=False):
+                 max_plies=300, random_play=False, streams=1):
         # random_play: RandomPolicy self-play (random_policy.py:25-41) -- no
         # search, uniform move choice and uniform moves_prob at every ply;
         # how the reference fills the replay buffer before training
@@ -91,6 +91,13 @@ class LockstepSelfPlay:
                 evaluator.to(self.device)
                 evaluator.prepare_inference()
             torch.backends.cudnn.benchmark = True
+        # streams > 1 (experimental): the games are split into that many windows driven on
+        # separate streams, so the tree kernels of one window run under the evaluator of
+        # another (az_engine_set_window); results do not depend on it.  Exact and 3.4 % faster
+        # with the network in the loop, but long runs with two evaluators in flight have
+        # failed: keep 1 outside experiments.
+        self.streams = max(1, min(int(streams), self.G))
+        self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.streams - 1)]
         self.moves_done = 0
         self._graph = None
         self._want_graph = bool(cuda_graph)
@@ -99,36 +106,63 @@ class LockstepSelfPlay:
             + (1 if self.is_stub else 0)
 
     # ------------------------------------------------------------ one move --
-    def _evaluate(self, root):
-        """Leaves -> (value, prior/logits, kind)."""
+    def _evaluate(self, root, g0=0, g1=None):
+        """Leaves of games [g0, g1) -> (value, prior/logits, kind)."""
         eng = self.eng
+        g1 = self.G if g1 is None else g1
         if self.is_stub:
             eng.stub_eval(self.evaluator.mode)
             return None, None, _cabi.AZ_PRIOR_PROBS
         if root:
-            value, logits = self.evaluator.evaluate_cells(eng.leaf_board[:, 0])
-            eng.prior[:, 0].copy_(logits)
+            value, logits = self.evaluator.evaluate_cells(eng.leaf_board[g0:g1, 0])
+            eng.prior[g0:g1, 0].copy_(logits)
             return None, None, _cabi.AZ_PRIOR_LOGITS
-        cells = eng.leaf_board.view(self.G * self.batch, eng.cell_stride)
+        cells = eng.leaf_board[g0:g1].view((g1 - g0) * self.batch, eng.cell_stride)
         value, logits = self.evaluator.evaluate_cells(cells)
         return value.contiguous(), logits.contiguous(), _cabi.AZ_PRIOR_LOGITS
 
-    def _move_body(self):
+    def _window_body(self, g0, g1):
+        """One move of games [g0, g1) on the current stream (the engine's
+        window must be set to it)."""
         eng = self.eng
         eng.select_root()
-        _, _, kind = self._evaluate(True)
+        _, _, kind = self._evaluate(True, g0, g1)
         eng.expand_root(None, kind)
         if self.random_play:
             eng.root_uniform()
         for _ in range(0 if self.random_play else self.num_batches):
             eng.select(self.batch, self.coef, self.noise_scale,
                        self.noise_alpha)
-            value, prior, kind = self._evaluate(False)
+            value, prior, kind = self._evaluate(False, g0, g1)
             eng.expand_backup(value, prior, kind)
             # keep evaluator outputs alive until the kernel that reads them
             # has been enqueued (same stream: safe to drop afterwards)
         eng.play_commit(self.temperature, self.depth, self.move_sampling,
                         self.collect_replay, True, self.chosen)
+
+    def _move_body(self):
+        if self.streams == 1:
+            return self._window_body(0, self.G)
+        eng = self.eng
+        main = torch.cuda.current_stream(self.device)
+        bounds = [self.G * i // self.streams for i in range(self.streams + 1)]
+        fork = torch.cuda.Event()
+        fork.record(main)
+        joins = []
+        for i in range(1, self.streams):
+            side = self._side[i - 1]
+            side.wait_event(fork)
+            with torch.cuda.stream(side):
+                eng.set_window(bounds[i], bounds[i + 1] - bounds[i])
+                self._window_body(bounds[i], bounds[i + 1])
+                done = torch.cuda.Event()
+                done.record(side)
+                joins.append(done)
+        eng.set_window(bounds[0], bounds[1] - bounds[0])
+        self._window_body(bounds[0], bounds[1])
+        eng.set_window(0, 0)
+        for done in joins:
+            main.wait_event(done)
 
     def capture(self):
         """Capture one move as a CUDA graph (capturing does not execute)."""

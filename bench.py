@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument('--skip-tree-only', action='store_true')
     ap.add_argument('--sims', type=int, default=800, help='simulations per move')
     ap.add_argument('--nodes-per-game', type=int, default=0)
+    ap.add_argument('--streams', type=int, default=1,
+                    help='windows of the games driven on separate streams (experimental, see DESIGN.md 5)')
     args = ap.parse_args()
     SEARCH['simulations'] = args.sims
     return args
@@ -296,6 +298,7 @@ def run_ours(args):
                           seed=0xBAD5EED5, rank=rank, world_size=world,
                           device=dev, cuda_graph=not args.no_graph,
                           collect_replay=True,
+                          streams=args.streams if args.evaluator == 'net' else 1,
                           nodes_per_game=args.nodes_per_game or None, **SEARCH)
     G, per_move = args.games, sp.sims_per_move
 
@@ -520,7 +523,7 @@ def run_ours(args):
             'config': {'workload': workload_name(args), 'board_size': args.board,
                        'games_per_gpu': G, 'sims_per_move': per_move,
                        'l2_policy': 'working set (node pools, > 1 GB) exceeds the 126 MB L2',
-                       'cuda_graph': not args.no_graph, **SEARCH},
+                       'cuda_graph': not args.no_graph, 'streams': sp.streams, **SEARCH},
             'moves_per_sec': moves_per_sec,
             'clocks': clk.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT,

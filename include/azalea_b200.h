@@ -132,6 +132,17 @@ int az_replay_row_bytes(const az_engine *e);
 
 /* ------------------------------------------------------------------ games */
 
+/* Restrict the per-game entry points below (everything that launches one warp
+ * per game: reset, hex_*, mcts_*, leaf_moves, root_stats, tree_move, stub_eval,
+ * play_commit) to the games [first_game, first_game + num_games); num_games <=
+ * 0 restores the full range.  Per-game arrays owned by the engine or sized
+ * [G] by the caller keep their absolute indexing; the value / prior arrays
+ * handed to az_mcts_expand_backup hold the window's rows only.  The window is
+ * read at launch time, so two halves of the games can be driven on two
+ * streams: the tree kernels of one half run under the evaluator of the other
+ * (selfplay.LockstepSelfPlay(streams=2)). */
+int az_engine_set_window(az_engine *e, int first_game, int num_games);
+
 /* HexGame.reset + Policy.reset for the games whose mask byte is non-zero
  * (NULL = all), hex.py:47-49, policy.py:72-76, search_tree.py:59-71. */
 int az_games_reset(az_engine *e, const uint8_t *mask_dev, void *stream);

@@ -603,3 +603,28 @@ def test_tcgen05_evaluator_against_reference_network_golden():
         idx = torch.from_numpy(moves[i, :k].astype(np.int64) - 1).cuda()
         logp = torch.log_softmax(logits[i, idx], 0).cpu().numpy()
         assert np.abs(logp - g['moves_logprob'][i, :k]).max() < 0.15, i
+
+
+@pytest.mark.parametrize('streams', (2, 3))
+def test_windowed_streams_do_not_change_the_games(streams):
+    """LockstepSelfPlay(streams=k) drives k windows of the games on k streams
+    (az_engine_set_window) so that tree kernels overlap the evaluator.  Games
+    are independent, so moves, results and replay rows are identical to the
+    single-stream run (stub evaluator: bit-exact), eager and graphed."""
+    from azalea_b200 import LockstepSelfPlay, StubEvaluator
+    from azalea_b200.engine import decode_replay_rows
+    def play(streams, graph):
+        sp = LockstepSelfPlay(StubEvaluator(2), num_games=50, board_size=5, simulations=40,
+                              search_batch_size=8, seed=11, streams=streams, cuda_graph=graph)
+        chosen = []
+        for _ in range(30):
+            sp.step_move()
+            chosen.append(sp.chosen.cpu().numpy().copy())
+        assert (sp.eng.status().cpu().numpy() == 0).all()
+        return np.stack(chosen), sp.harvest(), sp.counters()
+    c1, r1, n1 = play(1, False)
+    for graph in (False, True):
+        c2, r2, n2 = play(streams, graph)
+        assert np.array_equal(c1, c2)
+        assert r1.shape == r2.shape and np.array_equal(r1, r2)
+        assert n1 == n2

@@ -1062,7 +1062,7 @@ int64_t az_nn_tower_rows(int board_size, int64_t num_boards)
     return AZT_HALO + groups * board_size * 128 + 16;
 }
 
-static int azt_launch(azt_params &p, bool resid, bool heads, void *stream)
+static int azt_launch(azt_params &p, bool resid, void *stream)
 {
     static int debug = -1;                  /* probe switches (az_tower.cuh), read once */
     if (debug < 0) { const char *dbg = getenv("AZT_DEBUG"); debug = dbg ? atoi(dbg) : 0; }
@@ -1073,21 +1073,17 @@ static int azt_launch(azt_params &p, bool resid, bool heads, void *stream)
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        int rc = az_check(cudaFuncSetAttribute(k_conv3x3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
+        int rc = az_check(cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc == AZ_OK)
-            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
-        if (rc == AZ_OK)
-            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
+            rc = az_check(cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc != AZ_OK) return rc;
         attr_set = true;
     }
     const unsigned grid = (unsigned)(p.groups < sm_count ? p.groups : sm_count);
-    if (heads)
-        k_conv3x3<true, true><<<grid, AZT_THREADS_HEADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
-    else if (resid)
-        k_conv3x3<true, false><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    if (resid)
+        k_conv3x3<true><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     else
-        k_conv3x3<false, false><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+        k_conv3x3<false><<<grid, AZT_THREADS, AZT_SMEM_BYTES, (cudaStream_t)stream>>>(p);
     return az_check(cudaGetLastError());
 }
 
@@ -1102,35 +1098,7 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, c
     p.resid = (const uint8_t *)resid_dev; p.out = (uint8_t *)out_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
-    p.boards = num_boards;
-    return azt_launch(p, resid_dev != nullptr, false, stream);
-}
-
-int az_nn_conv3x3_heads(const void *x_dev, const void *w_dev, const float *bias_dev, const void *resid_dev,
-                        const float *heads_w_dev, const float *heads_b_dev, void *out_dev,
-                        int64_t out_board_stride, int heads, int board_size, int64_t num_boards, void *stream)
-{
-    if (!x_dev || !w_dev || !bias_dev || !resid_dev || !heads_w_dev || !heads_b_dev || !out_dev ||
-        board_size < 2 || board_size > 19 || num_boards < 0)
-        return AZ_E_INVALID;
-    if (heads != 6) return AZ_E_UNSUPPORTED;   /* value_chans 2 + policy_chans 4, network.py:123 */
-    if (out_board_stride == 0) out_board_stride = (int64_t)board_size * board_size * heads;
-    if (out_board_stride < board_size * board_size * heads || (out_board_stride & 1)) return AZ_E_INVALID;
-    if (num_boards == 0) return AZ_OK;
-    azt_params p = {};
-    p.x = (const uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
-    p.resid = (const uint8_t *)resid_dev; p.out = nullptr;
-    p.hout = (uint16_t *)out_dev; p.hstride = out_board_stride;
-    int rc = az_check(cudaMemcpyToSymbolAsync(azt_heads_const, heads_w_dev, 6 * 64 * sizeof(float), 0,
-                                              cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    if (rc == AZ_OK)
-        rc = az_check(cudaMemcpyToSymbolAsync(azt_heads_const, heads_b_dev, 6 * sizeof(float),
-                                              6 * 64 * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-    if (rc != AZ_OK) return rc;
-    p.n = board_size; p.bpg = 128 / (board_size + 1);
-    p.groups = (num_boards + p.bpg - 1) / p.bpg;
-    p.boards = num_boards;
-    return azt_launch(p, true, true, stream);
+    return azt_launch(p, resid_dev != nullptr, stream);
 }
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)

@@ -60,9 +60,8 @@
 //   warps 8-15  epilogue group 1 (odd output slabs)
 //   warps 16,17 MMA issuers (even / odd input slabs)
 //   warp 18     one thread streams input slabs through a 4-stage ring
-//   warp 19     one thread bulk-loads residual slabs into the staging tiles
+//   warp 19     spare
 //   warp 20     one thread bulk-stores finished staging tiles
-//   (HEADS variant, last layer: warps 20-27 project the finished tiles onto the heads instead)
 #pragma once
 
 #include <cuda_bf16.h>
@@ -77,10 +76,9 @@
 #define AZT_CHUNK_ROWS 144          // 8 + 128 + 8
 #define AZT_CHUNK_BYTES (AZT_CHUNK_ROWS * AZT_ROW)
 #define AZT_OUT_BYTES (128 * AZT_ROW)
-#define AZT_OUT_STAGES 5            // staging slabs: residual in, finished slab out
+#define AZT_OUT_STAGES 5            // staging slabs for finished output
 #define AZT_SMEM_BYTES (AZT_WBYTES + AZT_STAGES * AZT_CHUNK_BYTES + AZT_OUT_STAGES * AZT_OUT_BYTES)
-#define AZT_THREADS 672            // 768 for the HEADS variant (four head warps instead of the storer)
-#define AZT_THREADS_HEADS 896
+#define AZT_THREADS 672
 #define AZT_BLOCKS 8                // TMEM ring: 8 x 64 columns
 
 struct azt_params {
@@ -89,11 +87,6 @@ struct azt_params {
     const float *bias;      // [64]
     const uint8_t *resid;   // residual input (same layout) or NULL
     uint8_t *out;           // output activations
-    // HEADS variant (last tower layer): the 64 -> 6 head projection + ReLU of the finished slab
-    // goes to hout[board * hstride + tile * 6 + head] (bf16) instead of `out`
-    uint16_t *hout;
-    long long hstride;      // elements between boards in hout
-    long long boards;       // boards that exist (the last group may be partial)
     int n;                  // board size
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
@@ -179,6 +172,29 @@ __device__ __forceinline__ void azt_mma(uint32_t d, uint64_t da, uint64_t db, ui
           "=r"(v[14]), "=r"(v[15])                                                                 \
         : "r"(addr))
 
+// 32 bytes (one sector) in one request: the two 16-byte chunks 2m, 2m+1 of a row
+__device__ __forceinline__ void azt_ldg_sector(const void *p, uint4 &lo, uint4 &hi)
+{
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.b64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    lo = make_uint4((uint32_t)a, (uint32_t)(a >> 32), (uint32_t)b, (uint32_t)(b >> 32));
+    hi = make_uint4((uint32_t)c, (uint32_t)(c >> 32), (uint32_t)d, (uint32_t)(d >> 32));
+}
+
+// logical chunks 4 half .. 4 half + 3 of a swizzled row (chunk j at j ^ sw) -> r[0..3]: two
+// whole sectors, each requested once (four 16-byte loads would ask L2 for every sector twice)
+__device__ __forceinline__ void azt_load_resid(const uint8_t *row, int half, int sw, uint4 (&r)[4])
+{
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const int pair = ((half * 4 + 2 * m) ^ sw) >> 1;            // physical sector of logical chunks 2k, 2k+1
+        uint4 lo, hi;
+        azt_ldg_sector(row + pair * 32, lo, hi);
+        r[2 * m] = (sw & 1) ? hi : lo;
+        r[2 * m + 1] = (sw & 1) ? lo : hi;
+    }
+}
+
 __device__ __forceinline__ void azt_tmem_zero16(uint32_t addr)
 {
     const uint32_t z = 0u;
@@ -188,12 +204,8 @@ __device__ __forceinline__ void azt_tmem_zero16(uint32_t addr)
         ::"r"(addr), "r"(z) : "memory");
 }
 
-// head weights [6][64] + bias [6] of the HEADS variant (copied device-to-device, stream-ordered,
-// by az_nn_conv3x3_heads before every launch)
-__constant__ float azt_heads_const[6 * 64 + 8];
-
-template <bool RESID, bool HEADS>
-__global__ void __launch_bounds__(AZT_THREADS_HEADS, 1)
+template <bool RESID>
+__global__ void __launch_bounds__(AZT_THREADS, 1)
 k_conv3x3(const azt_params p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -203,7 +215,7 @@ k_conv3x3(const azt_params p)
     __shared__ uint64_t bar_w, bar_in_full[AZT_STAGES];
     __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7 (the MMA runs at most 7 slabs ahead)
     __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
-    __shared__ uint64_t bar_out_full[AZT_OUT_STAGES], bar_out_empty[AZT_OUT_STAGES], bar_out_done[AZT_OUT_STAGES];
+    __shared__ uint64_t bar_out_empty[AZT_OUT_STAGES], bar_out_done[AZT_OUT_STAGES];
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(16) float s_bias[AZT_C];
 
@@ -214,8 +226,7 @@ k_conv3x3(const azt_params p)
         for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
         for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
         for (int i = 0; i < AZT_OUT_STAGES; i++) {
-            azt_mbar_init(&bar_out_full[i], 1);
-            azt_mbar_init(&bar_out_empty[i], HEADS ? 4 : 1);    // released by the storer (HEADS: by the four head warps)
+            azt_mbar_init(&bar_out_empty[i], 1);        // released by the storer
             azt_mbar_init(&bar_out_done[i], 8);         // one arrival per warp of the group that wrote the slab
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -249,63 +260,9 @@ k_conv3x3(const azt_params p)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
 
-    if (warp >= 20 && HEADS) {
-        // ---------------------------------------------------- head warps --
-        // Two groups of four warps (alternate slabs) project every finished slab 64 -> 6 (+ bias, ReLU) straight from its
-        // staging tile, one row per thread, on plain FMAs whose weight operands come from the
-        // constant bank (no weight loads at all).  Deliberately not mma.sync: legacy tensor
-        // instructions interleaved with the tcgen05 stream stall it (the mma.sync version of
-        // this block made the kernel 20 % slower than the unfused one).
-        const int hgrp = (warp - 20) >> 2;                         // two groups of four warps on alternate slabs
-        const int row = ((warp - 20) & 3) * 32 + lane, sw = row & 7;
-        const int bl = row / (n + 1), bx = row - bl * (n + 1);
-        const bool cell = bl < p.bpg && bx < n;                     // not a pad cell
-        const long long hoff = bl * p.hstride + bx * 6;
-        long long hgroup = g0;
-        for (int j = hgrp, y = hgrp; j < ((p.debug & 4) ? 0 : nslabs); j += 2, y += 2) {
-            if (y >= n) { y -= n; hgroup++; }
-            const int sb = j % AZT_OUT_STAGES;
-            azt_mbar_wait(&bar_out_done[sb], (j / AZT_OUT_STAGES) & 1);
-            const uint4 *srow = reinterpret_cast<const uint4 *>(s_out + sb * AZT_OUT_BYTES + row * AZT_ROW);
-            uint4 v[8];
-#pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) v[c8] = srow[c8 ^ sw];
-            // the next writer of this tile is a bulk copy (async proxy): order our reads before it
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) azt_mbar_arrive(&bar_out_empty[sb]);            // staging slab free again
-            float acc[6][2];
-#pragma unroll
-            for (int h = 0; h < 6; h++) acc[h][0] = acc[h][1] = 0.f;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) {
-                const uint32_t vw[4] = {v[c8].x, v[c8].y, v[c8].z, v[c8].w};
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const float f0 = __uint_as_float(vw[q] << 16), f1 = __uint_as_float(vw[q] & 0xffff0000u);
-#pragma unroll
-                    for (int h = 0; h < 6; h++) {
-                        // weights are constant-bank operands of the FMAs: no loads
-                        acc[h][0] = fmaf(f0, azt_heads_const[h * 64 + c8 * 8 + 2 * q], acc[h][0]);
-                        acc[h][1] = fmaf(f1, azt_heads_const[h * 64 + c8 * 8 + 2 * q + 1], acc[h][1]);
-                    }
-                }
-            }
-            if (cell && hgroup * p.bpg + bl < p.boards) {
-                float o[6];
-#pragma unroll
-                for (int h = 0; h < 6; h++) o[h] = fmaxf(acc[h][0] + acc[h][1] + azt_heads_const[6 * 64 + h], 0.f);
-                uint32_t *dst = reinterpret_cast<uint32_t *>(p.hout + hgroup * p.bpg * p.hstride + (long long)y * n * 6 + hoff);
-#pragma unroll
-                for (int h = 0; h < 3; h++) {
-                    __nv_bfloat162 hh = __floats2bfloat162_rn(o[2 * h], o[2 * h + 1]);
-                    dst[h] = *reinterpret_cast<uint32_t *>(&hh);
-                }
-            }
-        }
-    } else if (warp >= 20) {
+    if (warp >= 20) {
         // -------------------------------------------------------- storer --
-        if (warp == 20 && lane == 0 && !(p.debug & 4)) {
+        if (lane == 0 && !(p.debug & 4)) {
             for (int j = 0; j < nslabs; j++) {
                 const int sb = j % AZT_OUT_STAGES;
                 azt_mbar_wait(&bar_out_done[sb], (j / AZT_OUT_STAGES) & 1);
@@ -320,16 +277,7 @@ k_conv3x3(const azt_params p)
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp == 19) {
-        // ----------------------------------------------- residual loader --
-        if (RESID && lane == 0 && !(p.debug & 4)) {
-            for (int j = 0; j < nslabs; j++) {
-                const int sb = j % AZT_OUT_STAGES;
-                azt_mbar_wait(&bar_out_empty[sb], ((j / AZT_OUT_STAGES) & 1) ^ 1);
-                azt_mbar_expect_tx(&bar_out_full[sb], AZT_OUT_BYTES);
-                azt_bulk_g2s(s_out + sb * AZT_OUT_BYTES,
-                             p.resid + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, AZT_OUT_BYTES, &bar_out_full[sb]);
-            }
-        }
+        // (spare warp)
     } else if (warp == 18) {
         // -------------------------------------------------- input loader --
         if (lane == 0) {
@@ -422,15 +370,25 @@ k_conv3x3(const azt_params p)
         const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
         const uint32_t keep = real ? 0xffffffffu : 0u;
         const int sw = l & 7;                                       // == R & 7 (8 + 128 q + l)
+        uint4 rnext[4];
+        if (RESID && grp < nslabs) {
+            azt_load_resid(p.resid + (size_t)(AZT_HALO + (q0 + grp) * 128 + l) * AZT_ROW, half, sw, rnext);
+        }
         for (int j = grp, y = grp % n; j < nslabs; j += 2, y = (y + 2) % n) {
             const int sb = j % AZT_OUT_STAGES;
             uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
-            if (!(p.debug & 4)) {
-                // the staging slab holds the residual (RESID) or must have been
-                // drained by the bulk store that used it last
-                if (RESID) azt_mbar_wait(&bar_out_full[sb], (j / AZT_OUT_STAGES) & 1);
-                else azt_mbar_wait(&bar_out_empty[sb], ((j / AZT_OUT_STAGES) & 1) ^ 1);
+            // the residual of this thread's row and channels comes straight from global memory,
+            // one slab of the group ahead: the loads for slab j + 2 fly while slab j is finished
+            uint4 rv[4];
+            if (RESID) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) rv[c] = rnext[c];
+                if (j + 2 < nslabs) {
+                    azt_load_resid(p.resid + (size_t)(AZT_HALO + (q0 + j + 2) * 128 + l) * AZT_ROW, half, sw, rnext);
+                }
             }
+            // the staging slab must have been drained by the bulk store that used it last
+            if (!(p.debug & 4)) azt_mbar_wait(&bar_out_empty[sb], ((j / AZT_OUT_STAGES) & 1) ^ 1);
             // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
             const int last = y + 1 < n ? j + 1 : j;
             azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1);
@@ -455,7 +413,7 @@ k_conv3x3(const azt_params p)
                     f[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
                     f[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
                     if (RESID) {
-                        const uint4 r = srow[c8 ^ sw];
+                        const uint4 r = rv[h * 2 + g];
                         const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
@@ -478,7 +436,7 @@ k_conv3x3(const azt_params p)
             __syncwarp();
             if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
             if (p.debug & 4) continue;
-            // staging slab complete: the storer sends it to global memory (HEADS: the head warps project it)
+            // staging slab complete: the storer sends it to global memory
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);

@@ -87,10 +87,6 @@ class HexNetwork(nn.Module):
         # 'cudnn': twelve fused cuDNN calls (also used for other widths)
         import os
         self.tower = os.environ.get('AZALEA_B200_TOWER', 'tcgen05')
-        # opt-in: the last tower layer also does the head projection
-        # (az_nn_conv3x3_heads); measured no faster than the separate heads
-        # kernel, so off by default
-        self.fuse_heads = os.environ.get('AZALEA_B200_FUSE_HEADS', '0') != '0'
         nnet = sum(p.nelement() for p in self.parameters())
         nenc = sum(p.nelement() for p in self.encoder.parameters())
         logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)
@@ -301,8 +297,8 @@ class HexNetwork(nn.Module):
     def _evaluate_cells_tcgen05(self, cells):
         """evaluate_cells with the whole tower on our tcgen05 convolution
         (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the slab
-        activation layout (residual added in the epilogue, in place; the last
-        one also projects onto the heads, az_nn_conv3x3_heads) -> one GEMM."""
+        activation layout (residual added in the epilogue, in place) -> heads
+        kernel -> one GEMM."""
         import ctypes
         from . import _cabi
         f = self._fast
@@ -330,32 +326,23 @@ class HexNetwork(nn.Module):
 
         wfc, bfc = f['fc_pad']
 
-        def conv(src, w, b, res, dst, heads=False):
+        def conv(src, w, b, res, dst):
             if ev is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(cur)
-            if heads:
-                # last layer: the head projection runs on the finished slab in shared
-                # memory, only the head activations are written
-                _cabi.check(L.az_nn_conv3x3_heads(p(src), p(w), p(b), p(res), p(f['heads_w32']),
-                                                  p(f['heads_b32']), p(flat), flat.shape[1], 6,
-                                                  n, npad, stream))
-            else:
-                _cabi.check(L.az_nn_conv3x3(p(src), p(w), p(b), p(res) if res is not None else None,
-                                            p(dst), n, npad, stream))
+            _cabi.check(L.az_nn_conv3x3(p(src), p(w), p(b), p(res) if res is not None else None,
+                                        p(dst), n, npad, stream))
             if ev is not None:
                 e1.record(cur)
-                ev.append((e0, e1, res is not None, N, heads))
-        last = len(f['tower']) - 1
-        for i, ((w1, b1), (w2, b2)) in enumerate(f['tower']):
+                ev.append((e0, e1, res is not None, N))
+        for (w1, b1), (w2, b2) in f['tower']:
             conv(x, w1, b1, None, y)
-            conv(y, w2, b2, x, x, heads=(i == last and self.fuse_heads))
+            conv(y, w2, b2, x, x)
         # head activations with the board row padded to a multiple of 8 (zeros):
         # the merged FC GEMM then runs a current cuBLAS kernel (K = 726 falls
         # back to a legacy one, 0.15 ms instead of 0.03)
-        if not self.fuse_heads or not f['tower']:
-            _cabi.check(L.az_nn_heads(p(x), N * n * n, p(f['heads_w32']), p(f['heads_b32']),
-                                      p(flat), flat.shape[1], 64, 6, n, stream))
+        _cabi.check(L.az_nn_heads(p(x), N * n * n, p(f['heads_w32']), p(f['heads_b32']),
+                                  p(flat), flat.shape[1], 64, 6, n, stream))
         yfc = F.linear(flat, wfc, bfc)
         k2 = f['nfc2']
         value = torch.tanh(F.linear(F.relu(yfc[:, :k2]), *f['value_fc3'])).squeeze(1)

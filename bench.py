@@ -427,11 +427,9 @@ def run_ours(args):
         # n*n cells x 64 channels x 2 B read + as much written, + as much again
         # for the residual of the second convolution of a block.
         cell_bytes = args.board * args.board * 128
-        # (the fused last layer reads two units and writes only the head activations)
-        cbytes = sum(boards * (cell_bytes * (2 if heads else 3 if res else 2) + (12 * args.board * args.board if heads else 0))
-                     for _, _, res, boards, heads in conv_ev)
-        cflop = sum(boards * args.board * args.board * 2 * 64 * 576 for _, _, _, boards, _ in conv_ev)
-        cms = sum(a.elapsed_time(b) for a, b, _, _, _ in conv_ev)
+        cbytes = sum(boards * cell_bytes * (3 if res else 2) for _, _, res, boards in conv_ev)
+        cflop = sum(boards * args.board * args.board * 2 * 64 * 576 for _, _, _, boards in conv_ev)
+        cms = sum(a.elapsed_time(b) for a, b, _, _ in conv_ev)
         conv_traffic = None
         try:
             conv_traffic = tj['k_conv3x3'][f'{args.board}x{args.board}/{G * sp.batch}']['traffic_bytes']
@@ -445,9 +443,9 @@ def run_ours(args):
             'traffic': conv_traffic, 'peak_source': peak_src,
             'launches_timed': len(conv_ev), 'avg_launch_ms': cms / len(conv_ev),
             'alg_bytes_per_launch': cbytes / len(conv_ev),
-            'avg_launch_ms_plain': (sum(a.elapsed_time(b) for a, b, r, _, _ in conv_ev if not r)
+            'avg_launch_ms_plain': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if not r)
                                     / max(1, sum(1 for e in conv_ev if not e[2]))),
-            'avg_launch_ms_residual': (sum(a.elapsed_time(b) for a, b, r, _, _ in conv_ev if r)
+            'avg_launch_ms_residual': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if r)
                                        / max(1, sum(1 for e in conv_ev if e[2]))),
             'useful_tflops': cflop / (cms * 1e-3) / 1e12,
             'tensor_peak_tflops_sustained': float(peaks.get('bf16_tflops_sustained', 1400.0)),

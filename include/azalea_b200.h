@@ -285,17 +285,7 @@ int64_t az_nn_tower_rows(int board_size, int64_t num_boards);   /* rows a buffer
 int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev,
                   const void *resid_dev, void *out_dev, int board_size,
                   int64_t num_boards, void *stream);
-/* The last tower layer fused with az_nn_heads (network.py:17-39 + :75-76,82-83):
- * the finished activations never leave the SM -- each 128-row slab is projected
- * 64 -> heads (= 6) + ReLU from shared memory and only out bf16
- * [board][out_board_stride] (tile-major, head-minor, as az_nn_heads writes it)
- * goes to memory.  resid is required (the layer is the second convolution of
- * a block); arguments as in az_nn_conv3x3 / az_nn_heads. */
-int az_nn_conv3x3_heads(const void *x_dev, const void *w_dev, const float *bias_dev,
-                        const void *resid_dev, const float *heads_w_dev,
-                        const float *heads_b_dev, void *out_dev,
-                        int64_t out_board_stride, int heads, int board_size,
-                        int64_t num_boards, void *stream);
+
 
 /* Test aid for the root exploration noise (mcts.py:126-131), which only has
  * statistical parity with RandomState.dirichlet: writes the Dirichlet(alpha)

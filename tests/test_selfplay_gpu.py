@@ -438,40 +438,6 @@ def test_tcgen05_conv3x3_matches_torch(n, N):
         assert rest == 0.0
 
 
-@pytest.mark.parametrize('n,N', ((11, 1029), (19, 9), (7, 91), (5, 1), (11, 4100)))
-def test_tcgen05_conv3x3_heads_fused(n, N):
-    """az_nn_conv3x3_heads (the last tower layer with the head projection done
-    on the finished slab in shared memory) against az_nn_conv3x3 followed by
-    az_nn_heads: same bf16 activations, fp32 accumulation in a different
-    order (rel 2^-7 + abs 1e-3); nothing is written past the real boards."""
-    import ctypes
-    from azalea_b200 import _cabi, tower_layout as tl
-    L = _cabi.lib()
-    torch.manual_seed(100 + n)
-    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
-    r = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
-    w = (torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16)
-    b = torch.randn(64, device='cuda') * 0.1
-    hw = torch.randn(6, 64, device='cuda') * 0.2
-    hb = torch.randn(6, device='cuda') * 0.1
-    xp, rp, wp = tl.to_slabs(x), tl.to_slabs(r), tl.pack_conv_weights(w)
-    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    p = lambda t: ctypes.c_void_p(t.data_ptr())
-    nn = n * n
-    stride = (nn * 6 + 7) // 8 * 8
-    out = torch.zeros_like(xp)
-    _cabi.check(L.az_nn_conv3x3(p(xp), p(wp), p(b), p(rp), p(out), n, N, stream))
-    want = torch.full((N + 1, stride), 7.0, dtype=torch.bfloat16, device='cuda')
-    _cabi.check(L.az_nn_heads(p(out), N * nn, p(hw), p(hb), p(want), stride, 64, 6, n, stream))
-    got = torch.full((N + 1, stride), 7.0, dtype=torch.bfloat16, device='cuda')
-    _cabi.check(L.az_nn_conv3x3_heads(p(xp), p(wp), p(b), p(rp), p(hw), p(hb), p(got), stride, 6,
-                                      n, N, stream))
-    torch.cuda.synchronize()
-    a, c = got[:N, :nn * 6].float(), want[:N, :nn * 6].float()
-    assert ((a - c).abs() <= c.abs() * 2 ** -7 + 1e-3).all(), float((a - c).abs().max())
-    assert (got[:N, nn * 6:] == 7.0).all() and (got[N] == 7.0).all()
-
-
 def test_tcgen05_tower_matches_cudnn_tower():
     """The whole evaluator with the tcgen05 tower (AZALEA_B200_TOWER=tcgen05)
     against the default cuDNN tower on the same weights: both are bf16 with

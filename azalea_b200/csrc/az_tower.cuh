@@ -72,11 +72,11 @@
 #define AZT_ROW 128                 // bytes per row
 #define AZT_HALO 8                  // zero rows in front of slab 0
 #define AZT_WBYTES (9 * 64 * 128)   // one layer's weights: [dx][dy][c_out][c_in]
-#define AZT_STAGES 4                // input ring
+#define AZT_STAGES 5                // input ring
 #define AZT_CHUNK_ROWS 144          // 8 + 128 + 8
 #define AZT_CHUNK_BYTES (AZT_CHUNK_ROWS * AZT_ROW)
 #define AZT_OUT_BYTES (128 * AZT_ROW)
-#define AZT_OUT_STAGES 5            // staging slabs for finished output
+#define AZT_OUT_STAGES 3            // staging slabs for finished output
 #define AZT_SMEM_BYTES (AZT_WBYTES + AZT_STAGES * AZT_CHUNK_BYTES + AZT_OUT_STAGES * AZT_OUT_BYTES)
 #define AZT_THREADS 672
 #define AZT_BLOCKS 8                // TMEM ring: 8 x 64 columns

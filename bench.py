@@ -301,6 +301,7 @@ def run_ours(args):
                           streams=args.streams if args.evaluator == 'net' else 1,
                           nodes_per_game=args.nodes_per_game or None, **SEARCH)
     G, per_move = args.games, sp.sims_per_move
+    n_streams = sp.streams
 
     # ---- warm-up (also captures the CUDA graph) ----
     for _ in range(max(3, args.warmup)):
@@ -521,7 +522,7 @@ def run_ours(args):
             'config': {'workload': workload_name(args), 'board_size': args.board,
                        'games_per_gpu': G, 'sims_per_move': per_move,
                        'l2_policy': 'working set (node pools, > 1 GB) exceeds the 126 MB L2',
-                       'cuda_graph': not args.no_graph, 'streams': sp.streams, **SEARCH},
+                       'cuda_graph': not args.no_graph, 'streams': n_streams, **SEARCH},
             'moves_per_sec': moves_per_sec,
             'clocks': clk.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT,

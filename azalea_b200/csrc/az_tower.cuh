@@ -20,11 +20,11 @@
 // (2) Pointer-shift taps, N = 192.  The input of tap dx for all 128 rows of
 // a slab is the same shared-memory tile with the UMMA descriptor start moved
 // by dx rows (the hardware swizzles on absolute address bits, any row offset
-// works: tools/probe/umma_probe.cu).  A 128xNx16 UMMA costs the same 71
-// cycles for N = 64 and N = 128 (tools/probe/umma_rate.cu), so 64 output
-// channels alone idle half the tensor pipe; here the three dy-taps of one dx
-// share the A operand against their stacked weights, N = 192 at full rate:
-// 12 MMAs per slab.
+// works: tools/probe/umma_probe.cu).  A 128xNx16 UMMA takes 64 cycles for
+// any N <= 128 (tools/probe/umma_seq.cu), so 64 output channels alone idle
+// half the tensor pipe; here the three dy-taps of one dx share the A operand
+// against their stacked weights, N = 192 at full rate (96 cycles): 12 MMAs
+// per slab.
 //
 // (3) TMEM accumulator ring.  Block dy of MMA(q) is the contribution of input
 // slab q to output slab q + 1 - dy -- at the same TMEM lane.  Accumulators are
@@ -39,9 +39,14 @@
 // finished slab leaves as one 16 KB bulk store.  The ring gives the epilogue
 // ~5 slabs of slack, so the tensor pipe never waits for it.
 //
-// Data movement is cp.async.bulk only: the layout is stored pre-swizzled in
-// global memory (16-byte chunk j of row R at chunk j ^ (R & 7)), so an input
-// slab plus its two neighbour rows is one contiguous 18 KB block.
+// Input and output move by cp.async.bulk: the layout is stored pre-swizzled
+// in global memory (16-byte chunk j of row R at chunk j ^ (R & 7)), so an
+// input slab plus its two neighbour rows is one contiguous 18 KB block.  The
+// residual is read by the epilogue threads themselves (one sector per
+// request); bulk-loading it into the staging tiles that the bulk stores read
+// from faulted when two instances of the kernel ran concurrently
+// (tools/probe/conv_concurrent.py), so those tiles only ever see generic
+// writes and bulk-store reads.
 //
 // (4) Nothing but MMAs on the issuing thread.  The tcgen05 pipe does not
 // queue ahead: every cycle the issuing thread spends on anything else
@@ -59,7 +64,7 @@
 //   warps 0-7   epilogue group 0 (even output slabs): warp = (32 channels, 32 rows)
 //   warps 8-15  epilogue group 1 (odd output slabs)
 //   warps 16,17 MMA issuers (even / odd input slabs)
-//   warp 18     one thread streams input slabs through a 4-stage ring
+//   warp 18     one thread streams input slabs through a 5-stage ring
 //   warp 19     spare
 //   warp 20     one thread bulk-stores finished staging tiles
 #pragma once

@@ -172,3 +172,20 @@ def test_tower_layout_helpers_roundtrip():
         for j in (0, 5):
             phys = j ^ (row & 7)
             assert torch.equal(wp[row, phys * 8:phys * 8 + 8], w[co, j * 8:j * 8 + 8, ky, kx])
+
+
+def test_policy_trainer_config_helpers():
+    """policy_trainer accepts both spellings of the reference's stale config
+    keys (config/hex11_train_config.yml vs policy_trainer.py:38-66) and
+    resolves the game class like the reference's import_and_get."""
+    from azalea_b200 import policy_trainer as pt
+    from azalea_b200.game.hex import HexGame
+    assert pt._cfg({'replaybuf_resample': 10}, 'replaybuf_oversampling', 'replaybuf_resample') == 10
+    assert pt._cfg({'replaybuf_oversampling': 4, 'replaybuf_resample': 10},
+                   'replaybuf_oversampling', 'replaybuf_resample') == 4
+    assert pt._cfg({}, 'a', 'b', default=7) == 7
+    with pytest.raises(KeyError):
+        pt._cfg({}, 'a', 'b')
+    assert pt._game_class('hex') is HexGame
+    assert pt._game_class('azalea.game.hex.HexGame') is HexGame
+    assert pt._game_class('azalea_b200.game.hex.HexGame') is HexGame

@@ -148,20 +148,22 @@ class LockstepSelfPlay:
         fork = torch.cuda.Event()
         fork.record(main)
         joins = []
-        for i in range(1, self.streams):
-            side = self._side[i - 1]
-            side.wait_event(fork)
-            with torch.cuda.stream(side):
-                eng.set_window(bounds[i], bounds[i + 1] - bounds[i])
-                self._window_body(bounds[i], bounds[i + 1])
-                done = torch.cuda.Event()
-                done.record(side)
-                joins.append(done)
-        eng.set_window(bounds[0], bounds[1] - bounds[0])
-        self._window_body(bounds[0], bounds[1])
-        eng.set_window(0, 0)
-        for done in joins:
-            main.wait_event(done)
+        try:
+            for i in range(1, self.streams):
+                side = self._side[i - 1]
+                side.wait_event(fork)
+                with torch.cuda.stream(side):
+                    eng.set_window(bounds[i], bounds[i + 1] - bounds[i])
+                    self._window_body(bounds[i], bounds[i + 1])
+                    done = torch.cuda.Event()
+                    done.record(side)
+                    joins.append(done)
+            eng.set_window(bounds[0], bounds[1] - bounds[0])
+            self._window_body(bounds[0], bounds[1])
+        finally:
+            eng.set_window(0, 0)        # the window is engine state: never leave it narrowed
+            for done in joins:
+                main.wait_event(done)
 
     def capture(self):
         """Capture one move as a CUDA graph (capturing does not execute)."""

@@ -14,7 +14,7 @@ import torch
 from . import _cabi
 from ._cabi import (AZ_BUF_COUNTERS, AZ_BUF_GLOBALS, AZ_BUF_LEAF_BOARD, AZ_BUF_LEAF_INFO,
                     AZ_BUF_LEAF_MOVES, AZ_BUF_META, AZ_BUF_PRIOR,
-                    AZ_BUF_REPLAY, AZ_BUF_VALUE, AZ_PRIOR_LOGITS,
+                    AZ_BUF_REPLAY, AZ_BUF_VALUE,
                     AZ_PRIOR_PROBS, COUNTER_NAMES, check)
 
 _DTYPES = {1: torch.int8, 4: torch.int32, 8: torch.int64}

@@ -17,7 +17,6 @@ independent: rank r of W owns global games [r*G, (r+1)*G), each game's
 Philox stream is keyed by its global id, so results do not depend on the
 world size.  The only exchange is the replay gather to rank 0.
 """
-from typing import Optional
 
 import numpy as np
 import torch

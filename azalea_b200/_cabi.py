@@ -16,12 +16,14 @@ AZ_OK = 0
 AZ_ST_POOL_FULL, AZ_ST_TREE_FULL, AZ_ST_ILLEGAL, AZ_ST_DISABLED = 1, 2, 4, 8
 AZ_LEAF_TERMINAL_KNOWN, AZ_LEAF_TERMINAL_NEW = 1, 2
 AZ_PRIOR_PROBS, AZ_PRIOR_LOGITS = 0, 1
+AZ_CFG_SOFT_POOL_FULL = 1
+AZ_ABI_VERSION = 2
 (AZ_BUF_LEAF_BOARD, AZ_BUF_LEAF_INFO, AZ_BUF_VALUE, AZ_BUF_PRIOR, AZ_BUF_META,
  AZ_BUF_REPLAY, AZ_BUF_COUNTERS, AZ_BUF_LEAF_MOVES, AZ_BUF_GLOBALS) = range(9)
 COUNTER_NAMES = ('simulations', 'sum_children', 'sum_depth', 'unique_leaves',
                  'expanded_children', 'plies', 'games', 'replay_rows',
                  'replay_dropped', 'games_failed', 'compacted_nodes',
-                 'nn_rows')
+                 'nn_rows', 'pool_skipped_expansions', 'terminal_leaves')
 ROW_HEADER_BYTES = 48
 
 
@@ -30,7 +32,8 @@ class AzConfig(C.Structure):
                 ('max_batch', C.c_int32), ('nodes_per_game', C.c_int32),
                 ('max_nodes_ref', C.c_int64), ('replay_rows', C.c_int32),
                 ('max_plies', C.c_int32), ('seed', C.c_uint64),
-                ('first_game_id', C.c_int64), ('game_id_stride', C.c_int64)]
+                ('first_game_id', C.c_int64), ('game_id_stride', C.c_int64),
+                ('flags', C.c_int32), ('reserved', C.c_int32)]
 
 
 class AzBufferDesc(C.Structure):
@@ -106,6 +109,8 @@ def lib():
     L.az_nn_stem.argtypes = [vp, C.c_int, C.c_int, C.c_int64, vp, f32p, vp, C.c_int,
                              C.c_int, vp]
     L.az_nn_heads.argtypes = [vp, C.c_int64, f32p, f32p, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
+    L.az_nn_tail.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
+                             f32p, C.c_int64, f32p, C.c_int64, vp]
     L.az_nn_tower_group.argtypes = [C.c_int]
     L.az_nn_tower_halo.argtypes = [C.c_int]
     L.az_nn_tower_rows.argtypes = [C.c_int, C.c_int64]

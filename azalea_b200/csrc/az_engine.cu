@@ -23,6 +23,38 @@ static int az_check(cudaError_t err)
     return AZ_E_CUDA;
 }
 
+// Kernels launch on the CURRENT device; an engine (and the stream the caller passes) belongs to
+// e->device.  Make that device current for the duration of the call when it is not already.
+struct az_device_guard {
+    int prev, changed;
+    explicit az_device_guard(int dev) : prev(dev), changed(0)
+    {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~az_device_guard() { if (changed) cudaSetDevice(prev); }
+};
+
+#define AZ_MAX_DEVICES 64
+
+// per-device facts for the engine-less evaluator kernels (they run on the current device)
+static int az_current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= AZ_MAX_DEVICES ? 0 : dev;
+}
+
+static int az_sm_count(int dev)
+{
+    static int cache[AZ_MAX_DEVICES];       // 0 = unknown; racing writers store the same value
+    if (cache[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n > 0 ? n : 148;
+    }
+    return cache[dev];
+}
+
 static inline int az_grid(const az_engine *e)
 {
     return (e->g1 - e->g0 + AZ_WARPS_PER_CTA - 1) / AZ_WARPS_PER_CTA;
@@ -30,6 +62,7 @@ static inline int az_grid(const az_engine *e)
 
 #define AZ_LAUNCH(kernel, e, stream, ...)                                              \
     do {                                                                               \
+        az_device_guard guard_((e)->device);                                           \
         kernel<<<az_grid(e), AZ_WARPS_PER_CTA * 32, 0, (cudaStream_t)(stream)>>>(*(e), \
                                                                       ##__VA_ARGS__); \
         return az_check(cudaGetLastError());                                           \
@@ -542,10 +575,20 @@ k_play_commit(az_engine e, az_play_params p, int32_t *chosen)
     // negated on the second player's
     if (p.collect_replay) {
         const int rows = min(nply, e.hist_rows);
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&e.globals[0], (unsigned long long)rows);
+        // reserve `rows` output rows; the cursor only ever advances by reservations that fit,
+        // so concurrent finishers can never be handed space beyond the capacity
+        unsigned long long base = ~0ull;
+        if (lane == 0) {
+            unsigned long long cur = *(volatile unsigned long long *)&e.globals[0];
+            for (;;) {
+                if (cur + (unsigned long long)rows > (unsigned long long)e.cfg.replay_rows) break;
+                const unsigned long long prev = atomicCAS(&e.globals[0], cur, cur + (unsigned long long)rows);
+                if (prev == cur) { base = cur; break; }
+                cur = prev;
+            }
+        }
         base = __shfl_sync(AZ_FULL, base, 0);
-        if (base + rows <= (unsigned long long)e.cfg.replay_rows) {
+        if (base != ~0ull) {
             const uint8_t *src = e.hist + (size_t)g * e.hist_rows * e.row_bytes;
             uint8_t *dst = e.replay + (size_t)base * e.row_bytes;
             const size_t n16 = (size_t)rows * e.row_bytes / 16;
@@ -561,7 +604,6 @@ k_play_commit(az_engine e, az_play_params p, int32_t *chosen)
             }
             if (lane == 0) cnt[AZ_CNT_REPLAY_ROWS] += rows;
         } else if (lane == 0) {
-            atomicAdd(&e.globals[0], (unsigned long long)(-(long long)rows));
             cnt[AZ_CNT_REPLAY_DROPPED] += rows;
         }
     }
@@ -754,8 +796,9 @@ int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_
     if (rc != AZ_OK) { free(e); return rc; }
     if (mem_bytes < e->total_bytes) { free(e); return AZ_E_NOMEM; }
     if (((uintptr_t)mem_dev & 255) != 0) { free(e); return AZ_E_INVALID; }
-    rc = az_check(cudaSetDevice(device));
-    if (rc != AZ_OK) { free(e); return rc; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { free(e); return AZ_E_INVALID; }
+    az_device_guard guard(device);
     e->device = device;
     char *base = (char *)mem_dev;
 #define AZ_BIND(field, type) e->field = (type)(base + (size_t)e->field)
@@ -776,6 +819,8 @@ int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_
 #undef AZ_BIND
     // scratch the evaluator reads even for unused slots must be defined
     rc = az_check(cudaMemsetAsync(e->leaf_board, 0, (size_t)e->G * e->B * e->cell_stride, 0));
+    // no leaves yet: node = -1 in every slot
+    if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->leaf_info, 0xff, (size_t)e->G * e->B * sizeof(int4), 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->meta, 0, (size_t)e->G * AZ_META_INTS * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->value, 0, (size_t)e->G * e->B * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->prior, 0, (size_t)e->G * e->B * e->nn * 4, 0));
@@ -935,6 +980,7 @@ int az_tree_move(az_engine *e, const int32_t *move_ids_dev, void *stream)
 int az_status(az_engine *e, int32_t *status_dev, void *stream)
 {
     if (!e || !status_dev) return AZ_E_INVALID;
+    az_device_guard guard(e->device);
     k_status<<<(e->G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*e, status_dev);
     return az_check(cudaGetLastError());
 }
@@ -982,15 +1028,16 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
     if (padded_layout) {
         const int bpg = 128 / (board_size + 1);
         const size_t smem = AZ_STEM_SLAB_SMEM(board_size, bpg);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[AZ_MAX_DEVICES];       // the opt-in is per device
+        const int dev = az_current_device();
+        if (!attr_set[dev]) {
             int rc = az_check(cudaFuncSetAttribute(k_nn_stem_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    AZ_STEM_SLAB_SMEM(19, 6)));
             if (rc != AZ_OK) return rc;
-            attr_set = true;
+            attr_set[dev] = true;
         }
         long long blocks = (num_boards + bpg - 1) / bpg;
-        if (blocks > 148 * 6) blocks = 148 * 6;
+        if (blocks > az_sm_count(dev) * 6) blocks = az_sm_count(dev) * 6;
         k_nn_stem_slab<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
             cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
             bias_dev, (uint16_t *)out_dev);
@@ -1042,6 +1089,26 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
     return az_check(cudaGetLastError());
 }
 
+int az_nn_tail(const void *y_dev, int64_t num_boards, int ld, int nfc2, int board_size,
+               const float *fc_bias_dev, const float *w3_dev, const float *b3_dev,
+               float *value_dev, int64_t value_stride, float *logits_dev, int64_t logits_stride,
+               void *stream)
+{
+    const int nn = board_size * board_size;
+    if (!y_dev || !fc_bias_dev || !w3_dev || !b3_dev || board_size < 2 || board_size > 19 ||
+        num_boards < 0 || nfc2 < 2 || (nfc2 & 1) || ld < nfc2 + nn || (ld & 1) ||
+        (logits_dev && logits_stride < nn) || (value_dev && value_stride < 1))
+        return AZ_E_INVALID;
+    if (num_boards == 0) return AZ_OK;
+    long long blocks = (num_boards + 7) / 8;
+    const int cap = az_sm_count(az_current_device()) * 16;
+    if (blocks > cap) blocks = cap;
+    k_nn_tail<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t *)y_dev, (long long)num_boards, ld, nfc2, nn, fc_bias_dev, w3_dev, b3_dev,
+        value_dev, (long long)value_stride, logits_dev, (long long)logits_stride);
+    return az_check(cudaGetLastError());
+}
+
 int az_nn_tower_group(int board_size)
 {
     /* boards that share one 128-row slab */
@@ -1067,17 +1134,15 @@ static int azt_launch(azt_params &p, bool resid, void *stream)
     static int debug = -1;                  /* probe switches (az_tower.cuh), read once */
     if (debug < 0) { const char *dbg = getenv("AZT_DEBUG"); debug = dbg ? atoi(dbg) : 0; }
     p.debug = debug;
-    static int sm_count = 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    static bool attr_set[AZ_MAX_DEVICES];           // the shared-memory opt-in is per device
+    const int dev = az_current_device();
+    const int sm_count = az_sm_count(dev);
+    if (!attr_set[dev]) {
         int rc = az_check(cudaFuncSetAttribute(k_conv3x3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc == AZ_OK)
             rc = az_check(cudaFuncSetAttribute(k_conv3x3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AZT_SMEM_BYTES));
         if (rc != AZ_OK) return rc;
-        attr_set = true;
+        attr_set[dev] = true;
     }
     const unsigned grid = (unsigned)(p.groups < sm_count ? p.groups : sm_count);
     if (resid)
@@ -1111,6 +1176,7 @@ int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, v
 int az_replay_clear(az_engine *e, void *stream)
 {
     if (!e) return AZ_E_INVALID;
+    az_device_guard guard(e->device);
     k_replay_clear<<<1, 32, 0, (cudaStream_t)stream>>>(*e);
     return az_check(cudaGetLastError());
 }

@@ -200,13 +200,16 @@ k_select(az_engine e, az_select_args a)
         return;
     }
 
+    // slots beyond this batch must not look like leaves to k_expand_backup,
+    // which walks all max_batch slots
+    if (lane >= a.batch && lane < e.B) info[lane] = make_int4(-1, 0, 0, 0);
     uint32_t *pathg = e.path + (size_t)g * e.B * e.path_stride;
     const uint2 key = make_uint2((uint32_t)e.cfg.seed ^ (uint32_t)meta[M_GID_LO],
                                  (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
     const int sim0 = meta[M_SIM];
     const int ply = meta[M_PLY];
     int my_leaf = -1, my_depth = 0;         // lane b remembers descent b
-    unsigned long long sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0;
+    unsigned long long sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0, term = 0;
 
     for (int b = 0; b < a.batch; b++) {
         uint32_t x = rx, o = ro, link = rootlink;
@@ -315,10 +318,12 @@ k_select(az_engine e, az_select_args a)
         int flags = 0, kk = 0;
         if (link != AZ_UNEVAL) {
             flags = AZ_LEAF_TERMINAL_KNOWN;
+            term++;
         } else {
             const int mover = 3 - color;    // who just played `tile`
             if (az_hex_wins(mover == 1 ? x : o, e.n, e.div_magic, tile, mover)) {
                 flags = AZ_LEAF_TERMINAL_NEW;
+                term++;
             } else {
                 kk = az_count_bits(~(x | o) & valid);
                 az_emit_board(e, smask, x, o, color == 2, lboard + (size_t)b * e.cell_stride);
@@ -353,6 +358,7 @@ k_select(az_engine e, az_select_args a)
         cnt[AZ_CNT_SUM_DEPTH] += sum_d;
         cnt[AZ_CNT_UNIQUE_LEAVES] += uniq;
         cnt[AZ_CNT_NN_ROWS] += nn_rows;
+        cnt[AZ_CNT_TERMINAL_LEAVES] += term;
     }
 }
 
@@ -375,7 +381,8 @@ k_expand_backup(az_engine e, az_expand_args a)
     const uint32_t valid = az_valid_word(lane, e.nn);
     int tail = meta[M_TAIL];
     long long vref = ((long long)(uint32_t)meta[M_VREF_LO]) | ((long long)meta[M_VREF_HI] << 32);
-    unsigned long long expanded = 0;
+    unsigned long long expanded = 0, skipped = 0;
+    const bool soft_full = (e.cfg.flags & AZ_CFG_SOFT_POOL_FULL) != 0;
 
     for (int b = 0; b < a.batch; b++) {
         const int4 inf = info[b];
@@ -386,10 +393,21 @@ k_expand_backup(az_engine e, az_expand_args a)
         // evaluate_batch, mcts.py:192-200: terminal positions are worth -1
         // to the player to move
         const float v = flags ? -1.0f : a.value[row];
-        if (!(flags & AZ_LEAF_TERMINAL_KNOWN)) {
+        bool expand = !(flags & AZ_LEAF_TERMINAL_KNOWN);
+        if (expand) {
             // create_child_nodes, search_tree.py:254-274
             if (vref + k > e.cfg.max_nodes_ref) { status |= AZ_ST_TREE_FULL; break; }
-            if (tail + k > e.C || tail + k > AZ_MAX_NODE) { status |= AZ_ST_POOL_FULL; break; }
+            if (tail + k > e.C || tail + k > AZ_MAX_NODE) {
+                // this half of the game's pool is exhausted (no reference analogue: its pool
+                // is MAX_NODES).  Soft mode: the leaf stays unevaluated -- its value is still
+                // backed up below, and a later visit expands it once the next re-root has
+                // compacted the pool; otherwise the game is flagged and dropped.
+                if (!soft_full) { status |= AZ_ST_POOL_FULL; break; }
+                expand = false;
+                skipped++;
+            }
+        }
+        if (expand) {
             const int fc = tail;
             if (k > 0) {
                 const float *prow = a.prior + row * e.nn;
@@ -465,6 +483,7 @@ k_expand_backup(az_engine e, az_expand_args a)
         meta[M_VREF_HI] = (int32_t)(vref >> 32);
         meta[M_STATUS] = status;
         e.counters[(size_t)g * AZ_CNT_PER_GAME + AZ_CNT_EXPANDED_CHILDREN] += expanded;
+        if (skipped) e.counters[(size_t)g * AZ_CNT_PER_GAME + AZ_CNT_POOL_SKIPPED] += skipped;
     }
 }
 

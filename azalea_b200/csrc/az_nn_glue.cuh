@@ -368,3 +368,41 @@ k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float 
                     az_pack_bf16x2(fmaxf(acc[2 * r] + bias0, 0.f), fmaxf(acc[2 * r + 1] + bias1, 0.f));
     }
 }
+
+// ---------------------------------------------------------------------------
+// k_nn_tail: everything after the merged fully connected GEMM, one warp per board.
+// y bf16 [N][ld] = (head activations) x (value_fc2 | move_fc)^T WITHOUT bias:
+//   columns [0, nfc2)           value_fc2 pre-activations  (network.py:78-79)
+//   columns [nfc2, nfc2 + nn)   move_fc logits over tiles  (network.py:145)
+// value  = tanh(value_fc3(relu(y[:nfc2] + bias)))            -> value[b * value_stride]
+// logits = y[nfc2:] + bias, fp32                             -> logits[b * logits_stride + tile]
+// The outputs go straight into the engine's AZ_BUF_VALUE / AZ_BUF_PRIOR rows (the
+// legal-move gather and softmax happen in k_expand_backup, AZ_PRIOR_LOGITS), so no
+// library elementwise kernel runs between the GEMM and the tree.
+__global__ void __launch_bounds__(256)
+k_nn_tail(const uint16_t *__restrict__ y, long long N, int ld, int nfc2, int nn,
+          const float *__restrict__ bias, const float *__restrict__ w3, const float *__restrict__ b3,
+          float *__restrict__ value, long long value_stride,
+          float *__restrict__ logits, long long logits_stride)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long b = warp; b < N; b += nwarps) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(y + b * ld);
+        float part = 0.f;
+        for (int c2 = lane; 2 * c2 < nfc2 + nn; c2 += 32) {
+            const uint32_t w = row[c2];
+            const float v[2] = {__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)};
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int c = 2 * c2 + h;
+                const float x = v[h] + bias[c];
+                if (c < nfc2) part = fmaf(fmaxf(x, 0.f), w3[c], part);
+                else if (c < nfc2 + nn && logits) logits[b * logits_stride + (c - nfc2)] = x;
+            }
+        }
+        for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+        if (value && lane == 0) value[b * value_stride] = tanhf(part + b3[0]);
+    }
+}

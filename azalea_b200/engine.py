@@ -34,12 +34,15 @@ class Engine:
     :param max_nodes_ref: the reference's ``search_tree.MAX_NODES``; a tree
         whose reference node count would exceed it is flagged
         ``AZ_ST_TREE_FULL`` (raised as ``SearchTreeFull`` by the front ends)
+    :param soft_pool_full: when a game's pool half is exhausted, skip the
+        expansion (counted in ``pool_skipped_expansions``) instead of
+        flagging ``AZ_ST_POOL_FULL``
     """
 
     def __init__(self, num_games, board_size=11, max_batch=10,
                  nodes_per_game=None, max_nodes_ref=10_000_000, replay_rows=0,
                  max_plies=300, seed=0, first_game_id=0, game_id_stride=0,
-                 device=None):
+                 device=None, soft_pool_full=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
@@ -62,7 +65,8 @@ class Engine:
             max_nodes_ref=int(max_nodes_ref), replay_rows=int(replay_rows),
             max_plies=int(max_plies), seed=int(seed) & (2 ** 64 - 1),
             first_game_id=int(first_game_id),
-            game_id_stride=int(game_id_stride))
+            game_id_stride=int(game_id_stride),
+            flags=_cabi.AZ_CFG_SOFT_POOL_FULL if soft_pool_full else 0)
         nbytes = self.lib.az_engine_device_bytes(C.byref(self.cfg))
         if nbytes == 0:
             raise ValueError('invalid engine configuration')
@@ -85,6 +89,25 @@ class Engine:
         self.replay = self._view(AZ_BUF_REPLAY, torch.uint8) \
             if replay_rows else None
         self.cell_stride = self.leaf_board.shape[-1]
+        self._spans = {}
+
+    def span(self, first, last):
+        """One contiguous uint8 view of the device block covering the buffers
+        from ``first`` to ``last`` (AZ_BUF_* ids, ``first`` before ``last`` in the
+        block) with everything between them, and each one's byte offset inside it: lets a host front end move
+        several small buffers with ONE copy."""
+        key = (first, last)
+        if key not in self._spans:
+            descs = {}
+            for which in range(_cabi.AZ_BUF_GLOBALS + 1):
+                d = _cabi.AzBufferDesc()
+                check(self.lib.az_engine_buffer(self._h, which, C.byref(d)))
+                descs[which] = (d.offset, d.bytes)
+            lo, hi = descs[first][0], descs[last][0] + descs[last][1]
+            assert lo < hi
+            inside = {w: (o - lo, b) for w, (o, b) in descs.items() if lo <= o and o + b <= hi}
+            self._spans[key] = (self.mem[lo:hi], inside)
+        return self._spans[key]
 
     def __del__(self):
         h = getattr(self, '_h', None)

@@ -6,19 +6,28 @@ plays ``num_rounds`` games, the first mover of each game is a coin flip from
 ``RandomState(10000 * round + s)``, and the result is ``{pair: [wins of i,
 draws, wins of j]}``.  The reference plays one game per worker process with
 two agents, two trees and two networks, and pushes every move into both trees
-(azalea/play_game.py:46-54).  Here all ``pairs x rounds`` games run in
-lockstep: one engine holds the first movers' trees, another the second
+(azalea/play_game.py:46-54).  Here all of a rank's ``(round, pair)`` games run
+in lockstep: one engine holds the first movers' trees, another the second
 movers'; at each ply the mover's engine searches, commits, and the move is
 replayed into the other engine (``tree_move`` + ``hex_step``).  Leaves are
 routed to the network of the policy that owns the tree.
 
+Sharding (the reference's ``parallel_compare`` fans the same tasks
+over worker processes, evaluation.py:49-58): task ``t = round * pairs + s``
+goes to rank ``t % world``; there is no exchange while the games run, and the
+``[pairs, 3]`` tallies are summed onto rank 0 with one ``reduce``.  Every
+game's random streams are keyed by its global task index, so the tallies do
+not depend on the world size.
+
 Moves are drawn on the device (per-game Philox streams) instead of from each
 agent's NumPy ``RandomState``: outcomes are statistically, not bitwise,
-comparable with the reference's.  ``RandomPolicy`` agents move uniformly at
-random without search (azalea/random_policy.py:25-41).
+comparable with the reference's; the searches themselves are bit-exact
+(tests/test_evaluation_gpu.py compares every tree with the oracle's).
+``RandomPolicy`` agents move uniformly at random without search
+(azalea/random_policy.py:25-41).
 """
 from collections import defaultdict
-from typing import Dict, List, Optional, Tuple
+from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
@@ -26,10 +35,10 @@ import torch
 from . import _cabi
 from .engine import Engine
 from .random_policy import RandomPolicy
-from .selfplay import StubEvaluator
+from .selfplay import StubEvaluator, default_nodes_per_game
 
 Pair = Tuple[int, int]
-M_STATUS = 5
+M_STATUS, M_GID_LO, M_GID_HI = 5, 10, 11
 
 
 def gen_pairs(num_players: int) -> List[Pair]:
@@ -54,7 +63,8 @@ def _policy_key(policy):
 class _Seat:
     """One engine = the trees of all games' first (or second) movers."""
 
-    def __init__(self, policies, board_size, seed, device, nodes_per_game):
+    def __init__(self, policies, board_size, seed, device, nodes_per_game,
+                 game_ids=None):
         self.policies = policies                # policy object per game
         G = len(policies)
         batch = max([p.search_batch_size for p in policies
@@ -62,11 +72,17 @@ class _Seat:
         sims = max([p.simulations for p in policies
                     if not isinstance(p, RandomPolicy)] + [1])
         if nodes_per_game is None:
-            nodes_per_game = 2 * (sims + batch + 1) * board_size ** 2
+            per_move = (sims // batch + 1) * batch
+            nodes_per_game = default_nodes_per_game(G, board_size ** 2, per_move, device)
         self.eng = Engine(G, board_size, max_batch=batch,
                           nodes_per_game=nodes_per_game, seed=seed,
-                          device=device)
+                          device=device, soft_pool_full=True)
         self.device = self.eng.device
+        if game_ids is not None:
+            # the Philox streams follow the game's global id, not its slot
+            ids = torch.as_tensor(np.asarray(game_ids, dtype=np.int64), device=self.device)
+            self.eng.meta[:, M_GID_LO] = (ids & 0xffffffff).to(torch.int32)
+            self.eng.meta[:, M_GID_HI] = (ids >> 32).to(torch.int32)
         self.chosen = torch.zeros(G, 4, dtype=torch.int32, device=self.device)
         # games grouped by search configuration, then by evaluator object
         self.groups = defaultdict(lambda: defaultdict(list))
@@ -84,8 +100,9 @@ class _Seat:
         self.index = {k: {nid: torch.tensor(gs, device=self.device)
                           for nid, gs in by_net.items()}
                       for k, by_net in self.groups.items()}
-        self.rng = torch.Generator(device=self.device)
-        self.rng.manual_seed(seed)
+        # test hook: called as on_search_done(seat, key, games) after a group's
+        # search and before its moves are committed
+        self.on_search_done: Optional[Callable] = None
 
     def _pause_all_but(self, games):
         pause = torch.full((self.eng.num_games,), _cabi.AZ_ST_DISABLED,
@@ -121,7 +138,16 @@ class _Seat:
             games = torch.cat(list(by_net.values()))
             self._pause_all_but(games)
             if key[0] == 'random':
-                self._random_moves(games)
+                # RandomPolicy.choose_action (random_policy.py:25-41) in terms of the
+                # tree: one visit on every child of the expanded root, then the
+                # temperature-1 draw of play_commit is uniform over the legal moves
+                eng.select_root()
+                eng.stub_eval(0)
+                eng.expand_root()
+                eng.root_uniform()
+                if self.on_search_done is not None:
+                    self.on_search_done(self, key, games)
+                eng.play_commit(1.0, 1 << 30, True, False, False, self.chosen)
                 continue
             sims, batch, coef, temp, depth, sampling, noise, alpha = key[:8]
             eng.select_root()
@@ -131,28 +157,11 @@ class _Seat:
                 eng.select(batch, coef, noise, alpha)
                 kind = self._evaluate(key, by_net, False)
                 eng.expand_backup(None, None, kind)
+            if self.on_search_done is not None:
+                self.on_search_done(self, key, games)
             eng.play_commit(temp, depth, sampling, False, False, self.chosen)
         self._resume_all()
         return self.chosen[:, 0].clone(), self.chosen[:, 1].clone()
-
-    def _random_moves(self, games):
-        """RandomPolicy.choose_action (random_policy.py:25-41) for `games`."""
-        eng = self.eng
-        moves, count = eng.hex_legal_moves()
-        count = count[games]
-        live = count > 0
-        u = torch.rand(len(games), device=self.device, generator=self.rng)
-        ordinal = torch.minimum((u * count).long(), (count - 1).clamp(min=0).long())
-        picked = moves[games].gather(1, ordinal[:, None]).squeeze(1)
-        step = torch.zeros(eng.num_games, dtype=torch.int32, device=self.device)
-        step[games] = torch.where(live, picked, torch.zeros_like(picked))
-        ids = -torch.ones(eng.num_games, dtype=torch.int32, device=self.device)
-        ids[games] = torch.where(live, ordinal.int(), -torch.ones_like(ordinal).int())
-        self._resume_all()
-        eng.tree_move(ids)
-        eng.hex_step(step)
-        self.chosen[games, 0] = step[games]
-        self.chosen[games, 1] = ids[games]
 
     def apply_opponent(self, moves, move_ids):
         """AzaleaAgent.execute_action for the opponent's move
@@ -163,15 +172,25 @@ class _Seat:
 
 def play_matches(first: List, second: List, board_size: int, seed: int = 0,
                  device=None, nodes_per_game: Optional[int] = None,
-                 game_max_length: int = 300):
+                 game_max_length: int = 300, game_ids=None, hook=None,
+                 stats: Optional[dict] = None):
     """Play len(first) games in lockstep; game g is first[g] (moves first)
     against second[g].  Returns (results int array: 3 first mover won, 1
-    second mover won, 2 draw; move history int32 [plies, G])."""
+    second mover won, 2 draw; move history int32 [plies, G]).
+
+    ``game_ids``: global id of every game (default: its index); a game's
+    random streams depend on (seed, id) only, not on which other games share
+    the engine.  ``hook``: test aid, see ``_Seat.on_search_done``.
+    ``stats``: optional dict that receives ``plies`` and ``simulations``."""
     assert len(first) == len(second)
-    seats = [_Seat(first, board_size, 2 * seed + 1, device, nodes_per_game),
-             _Seat(second, board_size, 2 * seed + 2, device, nodes_per_game)]
-    history = []
     G = len(first)
+    if G == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int32)
+    seats = [_Seat(first, board_size, 2 * seed + 1, device, nodes_per_game, game_ids),
+             _Seat(second, board_size, 2 * seed + 2, device, nodes_per_game, game_ids)]
+    for s in seats:
+        s.on_search_done = hook
+    history = []
     result = np.zeros(G, dtype=np.int64)
     for ply in range(min(game_max_length, board_size ** 2)):
         mover, other = seats[ply % 2], seats[1 - ply % 2]
@@ -184,37 +203,86 @@ def play_matches(first: List, second: List, board_size: int, seed: int = 0,
         assert not (bad & _cabi.AZ_ST_ILLEGAL).any(), 'inconsistent game state'
         if (res != 0).all():
             break
+    if stats is not None:
+        tot = [s.eng.counter_totals() for s in seats]
+        stats['plies'] = int(sum(int((h != 0).sum()) for h in history))
+        stats['simulations'] = sum(t['simulations'] for t in tot)
+        stats['pool_skipped_expansions'] = sum(t['pool_skipped_expansions'] for t in tot)
     result = np.where(result == 0, 2, result)       # play_game.py:57-61
     return result, np.stack(history)
 
 
-def evaluate(agents: List, num_rounds: int, num_workers: Optional[int] = None,
-             device=None) -> Dict[Pair, List[int]]:
-    """Round robin tournament between agents (evaluation.py:17-38).
-    ``num_workers`` is accepted for compatibility and ignored."""
-    pairs = gen_pairs(len(agents))
-    board_size = agents[0].game.board_size
-    first, second, meta = [], [], []
+def tournament_tasks(num_agents: int, num_rounds: int, rank: int = 0, world: int = 1):
+    """This rank's share of the tournament: [(task id, round, pair index,
+    pair, order)], task ``t = round * num_pairs + s`` on rank ``t % world``.
+    ``order`` is the reference's coin flip for the first move
+    (evaluation.py:67-76): +1 = pair[0] moves first."""
+    pairs = gen_pairs(num_agents)
+    out = []
     for r in range(num_rounds):
         for s, pair in enumerate(pairs):
-            # evaluation.py:67-76: coin flip for the first move
-            rng = np.random.RandomState(10000 * r + s)
-            order = rng.choice([-1, 1])
-            pa, pb = agents[pair[0]].policy, agents[pair[1]].policy
-            if order == 1:
-                first.append(pa)
-                second.append(pb)
-            else:
-                first.append(pb)
-                second.append(pa)
-            meta.append((pair, order))
-    result, _ = play_matches(first, second, board_size,
-                             seed=int(np.random.RandomState(num_rounds).randint(1 << 30)),
-                             device=device)
-    outcomes: Dict[Pair, List[int]] = defaultdict(lambda: [0, 0, 0])
-    for (pair, order), res in zip(meta, result):
-        outcome = order * (int(res) - 2)
-        outcomes[pair][0] += outcome > 0
-        outcomes[pair][1] += outcome == 0
-        outcomes[pair][2] += outcome < 0
-    return dict(outcomes)
+            t = r * len(pairs) + s
+            if t % world != rank:
+                continue
+            order = int(np.random.RandomState(10000 * r + s).choice([-1, 1]))
+            out.append((t, r, s, pair, order))
+    return out
+
+
+def _dist_info(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def evaluate(agents: List, num_rounds: int, num_workers: Optional[int] = None,
+             device=None, *, group=None, rank: Optional[int] = None,
+             world_size: Optional[int] = None, reduce: bool = True,
+             stats: Optional[dict] = None, _play=None) -> Dict[Pair, List[int]]:
+    """Round robin tournament between agents (evaluation.py:17-38).
+
+    ``num_workers`` is accepted for compatibility and ignored: under
+    ``torch.distributed`` the ranks take the role of the reference's worker
+    processes.  With a process group, rank 0 returns the tallies of the whole
+    tournament (one ``reduce`` of a ``[pairs, 3]`` tensor) and the other
+    ranks return their own share; ``rank`` / ``world_size`` override the
+    group's (``reduce=False``: no collective, this rank's share only).
+    """
+    r0, w0 = _dist_info(group)
+    rank = r0 if rank is None else rank
+    world = w0 if world_size is None else world_size
+    pairs = gen_pairs(len(agents))
+    tasks = tournament_tasks(len(agents), num_rounds, rank, world)
+    first, second = [], []
+    for _, _, _, pair, order in tasks:
+        pa, pb = agents[pair[0]].policy, agents[pair[1]].policy
+        first.append(pa if order == 1 else pb)
+        second.append(pb if order == 1 else pa)
+    board_size = agents[0].game.board_size
+    seed = int(np.random.RandomState(num_rounds).randint(1 << 30))
+    play = _play or play_matches
+    result, _ = play(first, second, board_size, seed=seed, device=device,
+                     game_ids=[t for t, *_ in tasks], stats=stats)
+    tally = np.zeros((len(pairs), 3), dtype=np.int64)
+    for (_, _, s, _, order), res in zip(tasks, result):
+        outcome = order * (int(res) - 2)            # evaluation.py:78-80
+        tally[s, 0 if outcome > 0 else (1 if outcome == 0 else 2)] += 1
+    if reduce and world > 1:
+        total = reduce_tallies(tally.copy(), group=group, device=device)
+        if rank == 0:
+            tally = total       # the other ranks keep (and return) their own share
+    return {pair: [int(x) for x in tally[s]] for s, pair in enumerate(pairs)}
+
+
+def reduce_tallies(tally: np.ndarray, dst: int = 0, group=None, device=None) -> np.ndarray:
+    """Sum the ranks' ``[pairs, 3]`` tallies onto rank ``dst`` (the path's
+    only exchange).  NCCL groups reduce a device tensor, gloo a host tensor."""
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    t = torch.from_numpy(np.ascontiguousarray(tally))
+    if 'nccl' in str(backend):
+        t = t.to(device if device is not None else
+                 torch.device('cuda', torch.cuda.current_device()))
+    dist.reduce(t, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return t.cpu().numpy()

@@ -87,6 +87,9 @@ class HexNetwork(nn.Module):
         # 'cudnn': twelve fused cuDNN calls (also used for other widths)
         import os
         self.tower = os.environ.get('AZALEA_B200_TOWER', 'tcgen05')
+        # one fused launch per residual block (csrc/az_block.cuh) instead of
+        # two az_nn_conv3x3 launches; AZALEA_B200_FUSED=0 keeps the two-launch path
+        self.tower_fused = os.environ.get('AZALEA_B200_FUSED', '1') != '0'
         nnet = sum(p.nelement() for p in self.parameters())
         nenc = sum(p.nelement() for p in self.encoder.parameters())
         logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)
@@ -221,13 +224,22 @@ class HexNetwork(nn.Module):
         fast['fc_pad'] = (keep(wpad), keep(bpad))
         fast['nfc2'] = w2.shape[0]
         fast['value_fc3'] = (keep(self.value_fc3.weight), keep(self.value_fc3.bias))
+        # operands of the tail kernel (csrc/az_nn_glue.cuh: k_nn_tail): the GEMM
+        # runs without bias, the fp32 bias is added where the results are
+        # converted to fp32
+        fast['fc_pad_t'] = fast['fc_pad'][0].t()
+        fast['fc_bias32'] = keep32(bpad)
+        fast['value_fc3_32'] = (keep32(self.value_fc3.weight.reshape(-1)),
+                                keep32(self.value_fc3.bias.reshape(-1)))
         self._fast = fast
         return self
 
     @torch.no_grad()
-    def evaluate_cells(self, cells):
+    def evaluate_cells(self, cells, value_out=None, logits_out=None,
+                       logits_stride=None, want_value=True):
         """int8 [N, >= n*n] network-view boards -> value f32 [N], logits
-        f32 [N, n*n] over tiles (no legal-move gather, no softmax)."""
+        f32 [N, n*n] over tiles (no legal-move gather, no softmax).  The
+        optional outputs are written in place (see _evaluate_cells_tcgen05)."""
         f = self._fast
         if f is None:
             raise RuntimeError('call prepare_inference() first')
@@ -238,7 +250,8 @@ class HexNetwork(nn.Module):
                 and C_ in (32, 64, 128) and cells.dtype == torch.int8
                 and cells.stride(1) == 1)
         if glue and self.tower == 'tcgen05' and f['tower'] is not None:
-            return self._evaluate_cells_tcgen05(cells)
+            return self._evaluate_cells_tcgen05(cells, value_out, logits_out,
+                                                logits_stride, want_value)
         if glue:
             # our kernels at both ends of the tower (csrc/az_nn_glue.cuh)
             from . import _cabi
@@ -291,32 +304,49 @@ class HexNetwork(nn.Module):
         k2 = f['nfc2']
         value = torch.tanh(F.linear(F.relu(y[:, :k2]), *f['value_fc3'])).squeeze(1)
         logits = y[:, k2:]
-        return value.float(), logits.float()
+        value, logits = value.float(), logits.float()
+        # comparison arms (cuDNN tower, fp32, CPU): honour the in-place outputs by copying
+        if value_out is not None:
+            value_out.copy_(value)
+            value = value_out
+        if logits_out is not None:
+            stride = int(logits_stride or n * n)
+            torch.as_strided(logits_out, (N, n * n), (stride, 1)).copy_(logits)
+            logits = logits_out
+        return value, logits
 
     @torch.no_grad()
-    def _evaluate_cells_tcgen05(self, cells):
+    def _evaluate_cells_tcgen05(self, cells, value_out=None, logits_out=None,
+                                logits_stride=None, want_value=True):
         """evaluate_cells with the whole tower on our tcgen05 convolution
         (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the slab
         activation layout (residual added in the epilogue, in place) -> heads
-        kernel -> one GEMM."""
+        kernel -> one GEMM -> tail kernel (bias, value head tail, fp32
+        outputs).  ``value_out`` f32 [N] / ``logits_out`` f32 rows of
+        ``logits_stride`` elements (default n*n, dense) receive the results in
+        place -- the lockstep path passes views of the engine's value / prior
+        buffers, so nothing is copied between the network and the tree."""
         import ctypes
         from . import _cabi
         f = self._fast
         L = _cabi.lib()
         n, N, dev = self.board_size, cells.shape[0], cells.device
+        nn2 = n * n
         npad = N
         rows = L.az_nn_tower_rows(n, N)
+        wfc, bfc = f['fc_pad']
         # one set of activation buffers per (batch size, stream): two halves of the games
-        # may be evaluated concurrently on two streams (selfplay.PipelinedSelfPlay)
+        # may be evaluated concurrently on two streams (LockstepSelfPlay(streams=2))
         stream_id = torch.cuda.current_stream(dev).cuda_stream
         bufs = f['tower_buf'].get((npad, dev, stream_id))
         if bufs is None:
             # halos and pad cells must be zero; the kernels keep them zero
             bufs = (torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
                     torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
-                    torch.zeros(N, f['fc_pad'][0].shape[1], dtype=torch.bfloat16, device=dev))
+                    torch.zeros(N, wfc.shape[1], dtype=torch.bfloat16, device=dev),
+                    torch.empty(N, wfc.shape[0], dtype=torch.bfloat16, device=dev))
             f['tower_buf'][(npad, dev, stream_id)] = bufs
-        x, y, flat = bufs
+        x, y, flat, yfc = bufs
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
@@ -324,26 +354,42 @@ class HexNetwork(nn.Module):
         ev = getattr(self, 'conv_events', None)     # bench.py: per-launch CUDA events
         cur = torch.cuda.current_stream(dev)
 
-        wfc, bfc = f['fc_pad']
+        def timed(fn, kind):
+            if ev is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(cur)
+            fn()
+            e1.record(cur)
+            ev.append((e0, e1, kind, N))
 
-        def conv(src, w, b, res, dst):
-            if ev is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(cur)
-            _cabi.check(L.az_nn_conv3x3(p(src), p(w), p(b), p(res) if res is not None else None,
-                                        p(dst), n, npad, stream))
-            if ev is not None:
-                e1.record(cur)
-                ev.append((e0, e1, res is not None, N))
-        for (w1, b1), (w2, b2) in f['tower']:
-            conv(x, w1, b1, None, y)
-            conv(y, w2, b2, x, x)
+        fused = f.get('tower_fused') if self.tower_fused else None
+        if fused is not None:
+            # one launch per residual block (csrc/az_block.cuh), in place
+            for w12, b12 in fused:
+                timed(lambda: _cabi.check(L.az_nn_resblock(
+                    p(x), p(w12), p(b12), n, npad, stream)), 'block')
+        else:
+            for (w1, b1), (w2, b2) in f['tower']:
+                timed(lambda: _cabi.check(L.az_nn_conv3x3(
+                    p(x), p(w1), p(b1), None, p(y), n, npad, stream)), 'plain')
+                timed(lambda: _cabi.check(L.az_nn_conv3x3(
+                    p(y), p(w2), p(b2), p(x), p(x), n, npad, stream)), 'residual')
         # head activations with the board row padded to a multiple of 8 (zeros):
         # the merged FC GEMM then runs a current cuBLAS kernel (K = 726 falls
         # back to a legacy one, 0.15 ms instead of 0.03)
-        _cabi.check(L.az_nn_heads(p(x), N * n * n, p(f['heads_w32']), p(f['heads_b32']),
+        _cabi.check(L.az_nn_heads(p(x), N * nn2, p(f['heads_w32']), p(f['heads_b32']),
                                   p(flat), flat.shape[1], 64, 6, n, stream))
-        yfc = F.linear(flat, wfc, bfc)
+        torch.mm(flat, f['fc_pad_t'], out=yfc)
         k2 = f['nfc2']
-        value = torch.tanh(F.linear(F.relu(yfc[:, :k2]), *f['value_fc3'])).squeeze(1)
-        return value.float(), yfc[:, k2:k2 + n * n].float()
+        if value_out is None and want_value:
+            value_out = torch.empty(N, dtype=torch.float32, device=dev)
+        if logits_out is None:
+            logits_out = torch.empty(N, nn2, dtype=torch.float32, device=dev)
+            logits_stride = nn2
+        w3, b3 = f['value_fc3_32']
+        _cabi.check(L.az_nn_tail(
+            p(yfc), N, yfc.shape[1], k2, n, p(f['fc_bias32']), p(w3), p(b3),
+            p(value_out) if value_out is not None else None, 1,
+            p(logits_out), int(logits_stride or nn2), stream))
+        return value_out, logits_out

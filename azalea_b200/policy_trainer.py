@@ -206,6 +206,10 @@ def initialize_replay_buffer(pool, game_factory: Callable, size: int, *,
     player.stop()
     buf = DeviceReplayBuffer(size, agent.game.board_size, device=rows.device)
     buf.put(rows[:size])
+    # ReplayBuffer(examples) starts with fresh_counter = 0 (replay_buffer.py:118):
+    # the initial rows do not count as fresh, so consume() asks the player for new
+    # self-play from the first training step on
+    buf.fresh_counter = 0
     logging.info(f'replaybuf initialized with {metrics["games"]} games '
                  f'and {len(buf)} examples')
     return buf

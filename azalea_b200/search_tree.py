@@ -187,11 +187,42 @@ class SearchTree:
         self._raise_if_full()
         return {'search_value': search_value / (num_batches * batch_size)}
 
+    def _host_buffers(self, eng):
+        """Persistent pinned staging for the two copies of a search batch:
+        leaf info + boards + legal moves come down in ONE device-to-host copy
+        (the three buffers are neighbours in the engine's block), values +
+        priors go up in ONE host-to-device copy."""
+        hb = getattr(self, '_hb', None)
+        if hb is None or hb['eng'] is not eng:
+            down, d_off = eng.span(_cabi.AZ_BUF_LEAF_INFO, _cabi.AZ_BUF_LEAF_MOVES)
+            up, u_off = eng.span(_cabi.AZ_BUF_VALUE, _cabi.AZ_BUF_PRIOR)
+            pin_down = torch.empty(down.numel(), dtype=torch.uint8).pin_memory()
+            pin_up = torch.zeros(up.numel(), dtype=torch.uint8).pin_memory()
+            B, nn, cs = eng.max_batch, eng.nn, eng.cell_stride
+            nd, nu = pin_down.numpy(), pin_up.numpy()
+
+            def view(buf, offs, which, dtype, shape):
+                o, b = offs[which]
+                return buf[o:o + b].view(dtype).reshape(shape)
+            hb = dict(eng=eng, down=down, up=up, pin_down=pin_down, pin_up=pin_up,
+                      info=view(nd, d_off, _cabi.AZ_BUF_LEAF_INFO, np.int32, (-1, B, 4))[0],
+                      board=view(nd, d_off, _cabi.AZ_BUF_LEAF_BOARD, np.int8, (-1, B, cs))[0],
+                      moves=view(nd, d_off, _cabi.AZ_BUF_LEAF_MOVES, np.int32, (-1, B, nn))[0],
+                      value=view(nu, u_off, _cabi.AZ_BUF_VALUE, np.float32, (-1, B))[0],
+                      prior=view(nu, u_off, _cabi.AZ_BUF_PRIOR, np.float32, (-1, B, nn))[0])
+            self._hb = hb
+        return hb
+
     def _evaluate(self, eng, game, net, rng):
         """mcts.evaluate_batch (mcts.py:155-217) for the leaves the select
         kernel just produced.  Returns the values in leaf-list order
-        (terminal rows included)."""
-        info = eng.leaf_info[0].cpu().numpy()
+        (terminal rows included).  One device-to-host copy + sync and one
+        host-to-device copy per search batch."""
+        hb = self._host_buffers(eng)
+        eng.compute_leaf_moves()
+        hb['pin_down'].copy_(hb['down'], non_blocking=True)
+        torch.cuda.current_stream(eng.device).synchronize()
+        info = hb['info']
         slots = np.flatnonzero(info[:, 0] >= 0)
         flags = info[slots, 1] & 0xff
         color = (info[slots, 1] >> 8) & 1
@@ -202,8 +233,8 @@ class SearchTree:
         if np.any(~term):
             live = slots[~term]
             n, nn = eng.n, eng.nn
-            boards = eng.leaf_board[0].cpu().numpy()[live, :nn]
-            moves = eng.compute_leaf_moves()[0].cpu().numpy()[live]
+            boards = hb['board'][live, :nn]
+            moves = hb['moves'][live]
             # prep.pad (prep.py:70-86): K = longest legal-move list in the
             # whole batch (terminal rows have none)
             K = int(info[slots, 2].max())
@@ -217,22 +248,21 @@ class SearchTree:
             # (hex.py:124-134)
             tbatch = {}
             for k in batch:
-                tbatch[k] = torch.tensor(batch[k])
+                tbatch[k] = torch.from_numpy(batch[k])
                 if net.device.type == 'cuda':
                     tbatch[k] = tbatch[k].pin_memory().to(net.device)
             output = net.run(tbatch)
             nonterm_value = output['value'].cpu().numpy()
             prior = np.exp(output['moves_logprob'].cpu().numpy())
-            assert all(prior.flat >= 0.0), 'negative prior prob'
-            assert all(abs(prior.sum(1) - 1.0).flat < 1e-4), \
+            assert (prior >= 0.0).all(), 'negative prior prob'
+            assert (np.abs(prior.sum(1) - 1.0) < 1e-4).all(), \
                 'prior probs normalized incorrectly'
             values[~term] = nonterm_value
-            val_dev = np.zeros(eng.max_batch, dtype=np.float32)
-            pri_dev = np.zeros((eng.max_batch, nn), dtype=np.float32)
-            val_dev[live] = nonterm_value
-            pri_dev[live, :prior.shape[1]] = prior
-            eng.value[0].copy_(torch.from_numpy(val_dev))
-            eng.prior[0].copy_(torch.from_numpy(pri_dev))
+            hb['value'][live] = nonterm_value
+            hb['prior'][live, :prior.shape[1]] = prior
+            # stream-ordered: the pinned buffer is next written after the next
+            # batch's synchronize, i.e. after this copy has completed
+            hb['up'].copy_(hb['pin_up'], non_blocking=True)
         return values
 
 

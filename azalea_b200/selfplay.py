@@ -28,6 +28,30 @@ from .search_tree import as_distribution
 from .typing import GameState
 
 
+def default_nodes_per_game(num_games, num_tiles, sims_per_move, device=None,
+                           keep_factor=4, memory_fraction=0.45):
+    """Capacity of each half of a game's node pool.
+
+    One move grows a tree by at most ``growth = (sims_per_move + 1) * n*n``
+    nodes (the reference materialises every child of an expanded leaf,
+    search_tree.py:254-274).  Re-rooting copies the kept subtree into the
+    other half, so the steady-state size is ``growth / (1 - f)`` with ``f``
+    the chosen child's share of the tree: ``keep_factor`` = 4 covers shares
+    up to 0.75, which peaked searches of a trained network reach at
+    temperature 0.  Capped so that all pools together use at most
+    ``memory_fraction`` of the device's free memory, and by the 23-bit node id.
+    """
+    growth = (sims_per_move + 1) * num_tiles
+    want = keep_factor * growth
+    try:
+        free, _ = torch.cuda.mem_get_info(device)
+        cap = int(memory_fraction * free) // (num_games * 2 * 16)
+        want = min(want, max(cap, growth + num_tiles + 1))
+    except Exception:
+        pass
+    return int(min(want, (1 << 23) - 1))
+
+
 class StubEvaluator:
     """Deterministic device stub (test / bench aid; modes as in
     oracle/azalea_oracle.h): 0 uniform, 1 dyadic, 2 rough."""
@@ -74,12 +98,16 @@ class LockstepSelfPlay:
         if replay_rows is None:
             replay_rows = 2 * self.G * min(self.nn, max_plies) if collect_replay else 0
         if nodes_per_game is None:
-            nodes_per_game = 2 * (self.sims_per_move + 1) * self.nn
+            nodes_per_game = default_nodes_per_game(
+                self.G, self.nn, self.sims_per_move, device)
+        # a full pool half never kills a game here: the expansion is skipped and
+        # counted (AZ_CFG_SOFT_POOL_FULL); see counters()['pool_skipped_expansions']
         self.eng = Engine(self.G, self.n, max_batch=self.batch,
                           nodes_per_game=nodes_per_game,
                           replay_rows=replay_rows, max_plies=max_plies,
                           seed=seed, first_game_id=rank * self.G,
-                          game_id_stride=world_size * self.G, device=device)
+                          game_id_stride=world_size * self.G, device=device,
+                          soft_pool_full=True)
         self.device = self.eng.device
         self.chosen = torch.zeros(self.G, 4, dtype=torch.int32,
                                   device=self.device)
@@ -111,13 +139,20 @@ class LockstepSelfPlay:
         if self.is_stub:
             eng.stub_eval(self.evaluator.mode)
             return None, None, _cabi.AZ_PRIOR_PROBS
+        # the evaluator's tail kernel writes fp32 value / logits straight into the
+        # engine's own value / prior rows of this window: nothing to copy, and
+        # expand_backup(None, None) reads them in place
         if root:
-            value, logits = self.evaluator.evaluate_cells(eng.leaf_board[g0:g1, 0])
-            eng.prior[g0:g1, 0].copy_(logits)
+            # leaf slot 0 of every game; the root's value is discarded (mcts.py:25-26)
+            self.evaluator.evaluate_cells(
+                eng.leaf_board[g0:g1, 0], logits_out=eng.prior[g0:g1, 0],
+                logits_stride=eng.max_batch * eng.nn, want_value=False)
             return None, None, _cabi.AZ_PRIOR_LOGITS
-        cells = eng.leaf_board[g0:g1].view((g1 - g0) * self.batch, eng.cell_stride)
-        value, logits = self.evaluator.evaluate_cells(cells)
-        return value.contiguous(), logits.contiguous(), _cabi.AZ_PRIOR_LOGITS
+        cells = eng.leaf_board[g0:g1].view((g1 - g0) * eng.max_batch, eng.cell_stride)
+        self.evaluator.evaluate_cells(
+            cells, value_out=eng.value[g0:g1].view(-1),
+            logits_out=eng.prior[g0:g1].view(-1, eng.nn), logits_stride=eng.nn)
+        return None, None, _cabi.AZ_PRIOR_LOGITS
 
     def _window_body(self, g0, g1):
         """One move of games [g0, g1) on the current stream (the engine's
@@ -163,6 +198,30 @@ class LockstepSelfPlay:
             eng.set_window(0, 0)        # the window is engine state: never leave it narrowed
             for done in joins:
                 main.wait_event(done)
+
+    def preroll(self, max_plies):
+        """Stagger the games: slot g is advanced by ``g * max_plies // G``
+        uniformly random plies (RandomPolicy moves, random_policy.py:25-41;
+        recorded as such in the replay rows), so that a lockstep run no longer
+        has every game at the same ply -- games end, restart, and reuse
+        subtrees at different times, as in steady-state self-play.  Eager;
+        call it before the move graph is captured or between replays."""
+        eng, G = self.eng, self.G
+        max_plies = int(max_plies)
+        try:
+            for s in range(1, max_plies + 1):
+                g0 = -(-s * G // max_plies)         # slots with quota >= s
+                if g0 >= G:
+                    break
+                eng.set_window(g0, G - g0)
+                eng.select_root()
+                eng.stub_eval(0)
+                eng.expand_root()
+                eng.root_uniform()
+                eng.play_commit(1.0, 1 << 30, True, self.collect_replay, True,
+                                self.chosen)
+        finally:
+            eng.set_window(0, 0)
 
     def capture(self):
         """Capture one move as a CUDA graph (capturing does not execute)."""

@@ -54,6 +54,14 @@ def parse_args():
     ap.add_argument('--nodes-per-game', type=int, default=0)
     ap.add_argument('--streams', type=int, default=1,
                     help='windows of the games driven on separate streams (opt-in, see DESIGN.md 5)')
+    ap.add_argument('--preroll', type=int, default=60,
+                    help='stagger the games before the steady-state window: slot g is advanced by '
+                         'g * PREROLL / G random plies (0 = time the opening only)')
+    ap.add_argument('--skip-configs', action='store_true',
+                    help='skip the config 1 / 4 / 5 legs (BASELINE.json configs[0], [3], [4])')
+    ap.add_argument('--c5-games', type=int, default=512)
+    ap.add_argument('--c5-sims', type=int, default=4000)
+    ap.add_argument('--c4-rounds', type=int, default=64, help='tournament rounds per GPU')
     args = ap.parse_args()
     SEARCH['simulations'] = args.sims
     return args
@@ -64,6 +72,13 @@ def workload_name(args):
         else f'stub evaluator mode {args.stub_mode}'
     return (f'Hex {args.board}x{args.board} lockstep self-play, {args.games} '
             f'concurrent games/GPU, {ev}, {args.sims} sims batch 10')
+
+
+def shared_config(args):
+    """`config` of the JSON line: identical for both arms (--impl ours / reference)."""
+    per_move = (args.sims // SEARCH['search_batch_size'] + 1) * SEARCH['search_batch_size']
+    return {'workload': workload_name(args), 'board_size': args.board,
+            'games_per_gpu': args.games, 'sims_per_move': per_move, **SEARCH}
 
 
 # ------------------------------------------------------------------ clocks --
@@ -235,11 +250,10 @@ def run_reference(args):
         'ms_per_step': 1e3 * tot_secs / max(1, args.steps),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': workload_name(args), 'board_size': args.board,
-                   **SEARCH},
+        'config': shared_config(args),
         'moves_per_sec': tot_plies / tot_secs,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads,
-                         'kind': 'port', 'sample': sample},
+                         'kind': 'port', 'sample': sample, **reference_python_figures()},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
@@ -256,6 +270,28 @@ def select_bytes(d, n):
     nw = (n * n + 31) // 32
     return (12 * d['sum_children'] + 8 * d['sum_depth'] + 32 * d['sum_depth']
             + 8 * nw * d['simulations'] + 4 * d['sum_depth'])
+
+
+def timed_steps(sp, steps, barrier, world, dev):
+    """K lockstep moves bracketed by barrier + synchronize; device time by CUDA
+    events on the launching stream, max over ranks.  Returns (ms, counter deltas)."""
+    import torch
+    import torch.distributed as dist
+    c0 = sp.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+        sp.step_move()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    c1 = sp.counters()
+    return ms, {k: c1[k] - c0[k] for k in c1}
 
 
 def run_ours(args):
@@ -287,6 +323,8 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured' if 'hbm_gbs' in peaks else 'fallback'
+    # kernels timed inside a long step: the sustained (power-capped) tensor figure
+    bf16_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
 
     if args.evaluator == 'net':
         torch.manual_seed(0)
@@ -302,39 +340,40 @@ def run_ours(args):
                           nodes_per_game=args.nodes_per_game or None, **SEARCH)
     G, per_move = args.games, sp.sims_per_move
     n_streams = sp.streams
+    steps = args.steps
 
     # ---- warm-up (also captures the CUDA graph) ----
     for _ in range(max(3, args.warmup)):
         sp.step_move()
     barrier()
 
-    # ---- timed region 1: device-resident, K steps ----
-    c0 = sp.counters()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- timed region 0: the opening (every game at the same early ply) ----
+    opening = None
     with ClockSampler(local) as clk:
-        barrier()
-        ev0.record()
-        for _ in range(args.steps):
-            sp.step_move()
-        ev1.record()
-        barrier()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    c1 = sp.counters()
-    d_run = {k: c1[k] - c0[k] for k in c1}
-    total_sims = world * G * per_move * args.steps
+        if args.preroll > 0:
+            ms0, d0 = timed_steps(sp, steps, barrier, world, dev)
+            opening = {'value': world * G * per_move * steps / (ms0 * 1e-3), 'unit': UNIT,
+                       'ms_per_step': ms0 / steps,
+                       'mean_depth': d0['sum_depth'] / max(1, d0['simulations']),
+                       'note': 'plies %d..%d of games started together from empty boards'
+                               % (max(3, args.warmup), max(3, args.warmup) + steps)}
+            # ---- stagger the games, then let the trees fill again ----
+            sp.preroll(args.preroll)
+            for _ in range(2):
+                sp.step_move()
+            barrier()
+        # ---- timed region 1: device-resident steady state, K steps ----
+        ms, d_run = timed_steps(sp, steps, barrier, world, dev)
+    total_sims = world * G * per_move * steps
     value = total_sims / (ms * 1e-3)
-    moves_per_sec = world * G * args.steps / (ms * 1e-3)
+    moves_per_sec = world * G * steps / (ms * 1e-3)
 
     # ---- timed region 2: end to end through the host-facing call ----
     # per step: new evaluator weights arrive from pinned host memory (the
     # trainer's hand-off; the reference pickles the whole agent per game,
     # parallel_player.py:36-38), the move runs, and the step's results --
     # every game's (move, move_id, result, ply) and the replay rows of the
-    # games that finished -- are read back to the host.
+    # games that finished -- are read back to the host (gathered to rank 0).
     h2d = d2h = 0
     if args.evaluator == 'net':
         host_w = [p.detach().float().cpu().pin_memory() for p in evaluator.parameters()]
@@ -346,7 +385,7 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     rows_out = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         if host_w:
             with torch.no_grad():
                 for p, w in zip(evaluator.parameters(), host_w):
@@ -401,9 +440,13 @@ def run_ours(args):
     launches = sp.num_batches
     sel_avg_ms = sel_ms / launches
     achieved = sel_bytes / launches / (sel_avg_ms * 1e-3) / 1e9
-    traffic = None
+    tj = {}
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    except Exception:
+        pass
+    traffic = None
+    try:
         key = f'{args.board}x{args.board}/{G}/' + ('noise' if sp.noise_scale else 'nonoise')
         traffic = tj['k_select'][key]['traffic_bytes']
     except Exception:
@@ -417,50 +460,21 @@ def run_ours(args):
         'alg_bytes_per_sim': sel_bytes / max(1, dk['simulations']),
         'mean_depth': dk['sum_depth'] / max(1, dk['simulations']),
         'mean_children': dk['sum_children'] / max(1, dk['sum_depth']),
-        'select_share_of_step': sel_ms / (ms / args.steps),
+        'select_share_of_step': sel_ms / (ms / steps),
         'expand_backup_avg_launch_ms': exp_ms / launches,
         'note': 'latency/occupancy-bound pointer chasing; see DESIGN.md',
     }
     roofline_tree = None
     if conv_ev:
-        # the dominant kernel of the step with the network evaluator: k_conv3x3
-        # (csrc/az_tower.cuh).  Algorithmic bytes per board and launch:
-        # n*n cells x 64 channels x 2 B read + as much written, + as much again
-        # for the residual of the second convolution of a block.
-        cell_bytes = args.board * args.board * 128
-        cbytes = sum(boards * cell_bytes * (3 if res else 2) for _, _, res, boards in conv_ev)
-        cflop = sum(boards * args.board * args.board * 2 * 64 * 576 for _, _, _, boards in conv_ev)
-        cms = sum(a.elapsed_time(b) for a, b, _, _ in conv_ev)
-        conv_traffic = None
-        try:
-            conv_traffic = tj['k_conv3x3'][f'{args.board}x{args.board}/{G * sp.batch}']['traffic_bytes']
-        except Exception:
-            pass
         roofline_tree = roofline
-        achieved_c = cbytes / (cms * 1e-3) / 1e9
-        roofline = {
-            'kernel': 'k_conv3x3', 'bound': 'hbm', 'achieved': achieved_c,
-            'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved_c / hbm_peak,
-            'traffic': conv_traffic, 'peak_source': peak_src,
-            'launches_timed': len(conv_ev), 'avg_launch_ms': cms / len(conv_ev),
-            'alg_bytes_per_launch': cbytes / len(conv_ev),
-            'avg_launch_ms_plain': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if not r)
-                                    / max(1, sum(1 for e in conv_ev if not e[2]))),
-            'avg_launch_ms_residual': (sum(a.elapsed_time(b) for a, b, r, _ in conv_ev if r)
-                                       / max(1, sum(1 for e in conv_ev if e[2]))),
-            'useful_tflops': cflop / (cms * 1e-3) / 1e12,
-            'tensor_peak_tflops_sustained': float(peaks.get('bf16_tflops_sustained', 1400.0)),
-            'conv_share_of_step': cms / (ms / args.steps),
-            'note': 'two launches per residual block: x->y (2 units of traffic) and y,x->x (3 units); '
-                    'the second sits on the HBM roofline, the first between HBM and the tensor pipe',
-        }
+        roofline = tower_roofline(conv_ev, args.board, G * sp.batch, ms / steps, hbm_peak,
+                                  bf16_peak, peak_src, 'bf16_tflops_sustained' in peaks, tj)
     nn_info = None
     if args.evaluator == 'net':
-        step_ms = ms / args.steps
-        rows = d_run['nn_rows'] / args.steps
+        step_ms = ms / steps
+        rows = d_run['nn_rows'] / steps
         padded = G * (per_move + 1)
         flop = NN_FLOP_PER_LEAF.get(args.board)
-        bf16_peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
         if flop:
             nn_ms = step_ms - (sel_ms + exp_ms)
             nn_info = {'useful_rows_per_step': rows, 'padded_rows_per_step': padded,
@@ -468,12 +482,14 @@ def run_ours(args):
                        'tflops_useful': rows * flop / (nn_ms * 1e-3) / 1e12,
                        'peak_bf16_tflops_sustained': bf16_peak,
                        'approx_nn_ms_per_step': nn_ms}
+    counters_total = sp.counters()
+    launches_per_step = sp_launches(args, per_move, evaluator)
 
     # ---- tree-only figure (stub evaluator) next to the headline ----
+    del sp, eng
+    torch.cuda.empty_cache()
     tree_only = None
     if args.evaluator == 'net' and not args.skip_tree_only:
-        del sp
-        torch.cuda.empty_cache()
         sp2 = LockstepSelfPlay(StubEvaluator(2), num_games=args.games,
                                board_size=args.board, seed=1, rank=rank,
                                world_size=world, device=dev, cuda_graph=True,
@@ -481,22 +497,30 @@ def run_ours(args):
                                nodes_per_game=args.nodes_per_game or None, **SEARCH)
         for _ in range(3):
             sp2.step_move()
-        barrier()
-        k2 = max(args.steps, 8)
-        ev0.record()
-        for _ in range(k2):
-            sp2.step_move()
-        ev1.record()
-        barrier()
-        ms2 = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms2], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms2 = float(t.item())
+        if args.preroll > 0:
+            sp2.preroll(args.preroll)
+            for _ in range(2):
+                sp2.step_move()
+        k2 = max(steps, 8)
+        ms2, d2 = timed_steps(sp2, k2, barrier, world, dev)
         tree_only = {'value': world * G * per_move * k2 / (ms2 * 1e-3), 'unit': UNIT,
                      'evaluator': 'device stub (mode 2)', 'ms_per_step': ms2 / k2,
-                     'moves_per_sec': world * G * k2 / (ms2 * 1e-3)}
+                     'moves_per_sec': world * G * k2 / (ms2 * 1e-3),
+                     'mean_depth': d2['sum_depth'] / max(1, d2['simulations']),
+                     'games_finished_per_step': d2['games'] / k2}
         del sp2
+        torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configurations, same JSON line ----
+    config5 = config4 = config1 = None
+    if not args.skip_configs:
+        config5 = guarded(lambda: bench_config5(args, rank, world, dev, barrier, hbm_peak, bf16_peak))
+        torch.cuda.empty_cache()
+        config4 = guarded(lambda: bench_config4(args, rank, world, dev, barrier))
+        torch.cuda.empty_cache()
+        if rank == 0:
+            config1 = guarded(lambda: bench_config1(dev))
+        barrier()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -509,39 +533,335 @@ def run_ours(args):
         cpu_baseline = {'value': r['sims'] / r['seconds'], 'unit': UNIT,
                         'cores': cores, 'kind': 'port', 'sample': r['sample'],
                         'seconds': r['seconds']}
+        cpu_baseline.update(reference_python_figures())
 
     if rank == 0:
+        failed = counters_total['games_failed']
+        skipped = counters_total['pool_skipped_expansions']
+        if failed or skipped:
+            print(f'WARNING: {failed} games dropped (tree/pool full), {skipped} expansions '
+                  f'skipped on a full pool -- raise --nodes-per-game', file=sys.stderr)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
-            'steps': args.steps, 'warmup': max(3, args.warmup),
-            'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'steps': steps, 'warmup': max(3, args.warmup),
+            'ms_per_step': ms / steps, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32 tree statistics (bit-exact PUCT); bf16 network'
             if args.evaluator == 'net' else 'f32',
             'data': 'synthetic',
-            'config': {'workload': workload_name(args), 'board_size': args.board,
-                       'games_per_gpu': G, 'sims_per_move': per_move,
-                       'l2_policy': 'working set (node pools, > 1 GB) exceeds the 126 MB L2',
-                       'cuda_graph': not args.no_graph, 'streams': n_streams, **SEARCH},
+            'config': shared_config(args),
+            'run': {'window': ('steady state: game slot g pre-rolled by g*%d/G random plies, so '
+                               'games end, restart and reuse subtrees inside the timed steps'
+                               % args.preroll) if args.preroll > 0 else 'opening',
+                    'l2_policy': 'working set (node pools, > 1 GB) exceeds the 126 MB L2',
+                    'cuda_graph': not args.no_graph, 'streams': n_streams,
+                    'tower': ('fused residual blocks' if getattr(evaluator, 'tower_fused', False)
+                              and getattr(evaluator, '_fast', {}).get('tower_fused') else 'two launches per block')
+                    if args.evaluator == 'net' else None},
             'moves_per_sec': moves_per_sec,
             'clocks': clk.summary(),
             'e2e': {'value': e2e_value, 'unit': UNIT,
-                    'h2d_bytes_per_step': h2d // max(1, args.steps),
-                    'd2h_bytes_per_step': d2h // max(1, args.steps),
-                    'ms_per_step': 1e3 * e2e_s / args.steps,
-                    'replay_rows_per_step': rows_out / args.steps},
-            'gpu_launches': args.steps * sp_launches(args, per_move, evaluator),
+                    'h2d_bytes_per_step': h2d // max(1, steps),
+                    'd2h_bytes_per_step': d2h // max(1, steps),
+                    'ms_per_step': 1e3 * e2e_s / steps,
+                    'replay_rows_per_step': rows_out / steps},
+            'gpu_launches': steps * launches_per_step,
             'roofline': roofline,
             'roofline_tree': roofline_tree,
             'cpu_baseline': cpu_baseline,
             'tree_only': tree_only,
+            'opening': opening,
             'network': nn_info,
-            'counters_per_step': {k: v / args.steps for k, v in d_run.items()},
+            'counters_per_step': {k: v / steps for k, v in d_run.items()},
+            'mean_depth': d_run['sum_depth'] / max(1, d_run['simulations']),
+            'games_failed_total': failed, 'pool_skipped_expansions_total': skipped,
+            'config1': config1, 'config4': config4, 'config5': config5,
         }
         print_json(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def guarded(fn):
+    """A side leg must never cost the headline line."""
+    try:
+        return fn()
+    except Exception as exc:        # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        return {'error': f'{type(exc).__name__}: {exc}'}
+
+
+def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_src,
+                   tensor_measured, tj):
+    """Roofline of the step's dominant kernel, the evaluator's tower
+    convolutions, from per-launch CUDA events.
+
+    Fused block (k_resblock, one launch per residual block): both
+    convolutions from one read and one write of the activations, so the
+    kernel is bound by the tensor pipe: useful FLOPs = 2 x 2*64*576 per cell.
+    Two-launch path (k_conv3x3): plain launch 2 units of HBM traffic,
+    residual launch 3."""
+    cell_bytes = board * board * 128
+    conv_flop = board * board * 2 * 64 * 576
+    kinds = {}
+    for e0, e1, kind, nb in conv_ev:
+        kinds.setdefault(kind, []).append((e0.elapsed_time(e1), nb))
+    tot_ms = sum(t for v in kinds.values() for t, _ in v)
+    n_launch = sum(len(v) for v in kinds.values())
+    units = {'plain': 2, 'residual': 3, 'block': 2}
+    convs = {'plain': 1, 'residual': 1, 'block': 2}
+    cbytes = sum(nb * cell_bytes * units[k] for k, v in kinds.items() for _, nb in v)
+    cflop = sum(nb * conv_flop * convs[k] for k, v in kinds.items() for _, nb in v)
+    tflops = cflop / (tot_ms * 1e-3) / 1e12
+    gbs = cbytes / (tot_ms * 1e-3) / 1e9
+    fused = 'block' in kinds
+    out = {
+        'kernel': 'k_resblock' if fused else 'k_conv3x3',
+        'launches_timed': n_launch, 'avg_launch_ms': tot_ms / n_launch,
+        'share_of_step': tot_ms / step_ms,
+        'useful_tflops': tflops, 'alg_gbs': gbs,
+        'alg_bytes_per_launch': cbytes / n_launch, 'alg_flop_per_launch': cflop / n_launch,
+        'per_kind_avg_ms': {k: sum(t for t, _ in v) / len(v) for k, v in kinds.items()},
+        'hbm_frac': gbs / hbm_peak, 'tensor_frac': tflops / bf16_peak,
+        'hbm_peak_gbs': hbm_peak, 'tensor_peak_tflops_sustained': bf16_peak,
+        'peak_source': peak_src if tensor_measured else 'fallback',
+    }
+    key = ('k_resblock' if fused else 'k_conv3x3')
+    try:
+        out['traffic'] = tj[key][f'{board}x{board}/{boards}']['traffic_bytes']
+    except Exception:
+        out['traffic'] = None
+    if fused:
+        out.update(bound='tensor', achieved=tflops, peak=bf16_peak, unit='TFLOP/s',
+                   frac=tflops / bf16_peak,
+                   note='one launch per residual block: 2 convolutions from one read + one write of '
+                        'the activations; useful FLOPs exclude the pad cells of the slab layout '
+                        '(110 of 128 MMA rows are real cells at 11x11); peak = sustained cuBLAS bf16')
+    else:
+        out.update(bound='hbm', achieved=gbs, peak=hbm_peak, unit='GB/s', frac=gbs / hbm_peak,
+                   note='two launches per residual block: x->y (2 units of traffic, close to the '
+                        'tensor ridge) and y,x->x (3 units, on the HBM roofline)')
+    return out
+
+
+def reference_python_figures():
+    """The UNMODIFIED Python/Numba reference, timed on the build box by
+    tools/measure_reference.py (it cannot travel to the GPU box)."""
+    try:
+        r = json.load(open(os.path.join(ROOT, 'profiles', 'r02_reference_python.json')))
+    except Exception:
+        return {}
+    out = {'reference_python_sims_per_s': r['one_process']['sims_per_s'],
+           'reference_python_s_per_move': r['one_process']['s_per_move'],
+           'reference_python_cores': 1,
+           'reference_python_box': f"{r['box']} ({r['cores']} cores), stub evaluator, "
+                                   'profiles/r02_reference_python.json'}
+    if 'process_pool' in r:
+        out['reference_python_pool_sims_per_s'] = r['process_pool']['sims_per_s']
+        out['reference_python_pool_workers'] = r['process_pool']['workers']
+    return out
+
+
+# ------------------------------------------------- BASELINE.json configs[4] --
+
+def bench_config5(args, rank, world, dev, barrier, hbm_peak, bf16_peak):
+    """Hex 19x19 deep-search stress test: many simulations per move, a node
+    pool sized for them, 6x64 network.  Every rank runs its own games (weak
+    scaling, like the headline)."""
+    import torch
+    from azalea_b200 import LockstepSelfPlay
+    from azalea_b200.network import HexNetwork
+    n, G, sims = 19, args.c5_games, args.c5_sims
+    torch.manual_seed(0)
+    net = HexNetwork(n, 6, 64).eval().to(dev)
+    net.prepare_inference(torch.bfloat16)
+    search = dict(SEARCH, simulations=sims)
+    sp = LockstepSelfPlay(net, num_games=G, board_size=n, seed=0xC0F165, rank=rank,
+                          world_size=world, device=dev, cuda_graph=True, collect_replay=True,
+                          **search)
+    per_move = sp.sims_per_move
+    for _ in range(3):
+        sp.step_move()
+    steps = 2
+    ms, d = timed_steps(sp, steps, barrier, world, dev)
+    # per-launch shares from one eager move
+    eng, stream = sp.eng, torch.cuda.current_stream()
+    conv_ev = net.conv_events = []
+    sel = []
+    eng.select_root()
+    sp._evaluate(True)
+    eng.expand_root(None, 1)
+    c0 = sp.counters()
+    for _ in range(sp.num_batches):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        eng.select(sp.batch, sp.coef, sp.noise_scale, sp.noise_alpha)
+        b.record(stream)
+        sp._evaluate(False)
+        eng.expand_backup(None, None, 1)
+        sel.append((a, b))
+    eng.play_commit(sp.temperature, sp.depth, sp.move_sampling, True, True, sp.chosen)
+    torch.cuda.synchronize()
+    net.conv_events = None
+    c1 = sp.counters()
+    dk = {k: c1[k] - c0[k] for k in c1}
+    sel_ms = sum(a.elapsed_time(b) for a, b in sel)
+    sel_b = select_bytes(dk, n)
+    tower = tower_roofline(conv_ev, n, G * sp.batch, ms / steps, hbm_peak, bf16_peak,
+                           'measured', True, {})
+    tot = sp.counters()
+    out = {'workload': f'Hex 19x19 deep search, {G} games/GPU, 6x64 resnet bf16, {sims} sims batch 10',
+           'value': world * G * per_move * steps / (ms * 1e-3), 'unit': UNIT,
+           'moves_per_sec': world * G * steps / (ms * 1e-3), 'ms_per_step': ms / steps,
+           'steps': steps, 'n_gpus': world, 'sims_per_move': per_move,
+           'nodes_per_game_half': eng.nodes_per_game,
+           'node_pool_gb_per_gpu': G * 2 * eng.nodes_per_game * 16 / 1e9,
+           'mean_depth': d['sum_depth'] / max(1, d['simulations']),
+           'mean_children': d['sum_children'] / max(1, d['sum_depth']),
+           'k_select12': {'avg_launch_ms': sel_ms / sp.num_batches,
+                          'alg_gbs': sel_b / (sel_ms * 1e-3) / 1e9,
+                          'hbm_frac': sel_b / (sel_ms * 1e-3) / 1e9 / hbm_peak,
+                          'share_of_step': sel_ms / (ms / steps)},
+           'tower': {k: tower[k] for k in ('kernel', 'avg_launch_ms', 'useful_tflops', 'alg_gbs',
+                                           'hbm_frac', 'tensor_frac', 'share_of_step')},
+           'games_failed': tot['games_failed'],
+           'pool_skipped_expansions': tot['pool_skipped_expansions']}
+    del sp, eng
+    return out
+
+
+# ------------------------------------------------- BASELINE.json configs[3] --
+
+def bench_config4(args, rank, world, dev, barrier):
+    """Round-robin tournament with compare() semantics (compare_cli.py:57-82,
+    evaluation.py:17-80): 4 random-init 6x64 policies + the <random> anchor = 5
+    agents, 10 pairs per round, move_sampling on, noise off, two trees per
+    game; (round, pair) games dealt round-robin to the ranks, tallies reduced
+    to rank 0.  Rounds scale with the world size (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import azalea_b200 as az
+    from azalea_b200.evaluation import evaluate, reduce_tallies, gen_pairs
+    n = args.board
+    agents = [az.AzaleaAgent(lambda: az.HexGame(n))]            # <random>, Elo anchor
+    for i in range(4):
+        torch.manual_seed(i)
+        p = az.Policy()
+        p.initialize(dict(device=str(dev), network='HexNetwork', board_size=n, num_blocks=6,
+                          base_chans=64, simulations=SEARCH['simulations'],
+                          search_batch_size=SEARCH['search_batch_size'],
+                          exploration_coef=SEARCH['exploration_coef'],
+                          exploration_depth=SEARCH['exploration_depth'],
+                          exploration_noise_alpha=SEARCH['exploration_noise_alpha'],
+                          exploration_noise_scale=SEARCH['exploration_noise_scale'],
+                          exploration_temperature=SEARCH['exploration_temperature']))
+        a = az.AzaleaAgent(lambda: az.HexGame(n), policy=p)
+        a.settings['move_sampling'] = True                      # compare_cli.py:70-71
+        agents.append(a)
+    rounds = args.c4_rounds * world
+    stats = {}
+    barrier()
+    t0 = time.perf_counter()
+    ok, share = 1, None
+    try:
+        share = evaluate(agents, rounds, rank=rank, world_size=world, reduce=False,
+                         device=dev, stats=stats)
+    except Exception:       # noqa: BLE001  keep the ranks in step: agree before the collective
+        import traceback
+        traceback.print_exc()
+        ok = 0
+    pairs = gen_pairs(len(agents))
+    if world > 1:
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item())
+    if not ok:
+        return {'error': 'a rank failed during the tournament'}
+    tally = np.array([share[pr] for pr in pairs], dtype=np.int64)
+    work = np.array([stats['plies'], stats['simulations'], len(share) and int(tally.sum())],
+                    dtype=np.int64)
+    if world > 1:
+        tally = reduce_tallies(tally, device=dev)
+        t = torch.from_numpy(work).to(dev)
+        dist.all_reduce(t)
+        work = t.cpu().numpy()
+    barrier()
+    secs = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([secs], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+    games = int(work[2])
+    return {'workload': f'Hex {n}x{n} round-robin tournament, 4 random-init 6x64 policies + <random>, '
+                        f'{rounds} rounds x 10 pairs, 800 sims batch 10, two trees per game',
+            'n_gpus': world, 'rounds': rounds, 'games': games, 'seconds': secs,
+            'games_per_sec': games / secs, 'moves_per_sec': int(work[0]) / secs,
+            'value': int(work[1]) / secs, 'unit': UNIT,
+            'sharding': 'task t = round * 10 + pair on rank t % world; [10, 3] tallies reduced to rank 0',
+            'timing': 'host wall clock around the whole tournament (eager launches, engines and '
+                      'evaluators set up inside), max over ranks',
+            'tallies': {f'{a}-{b}': [int(x) for x in tally[s]] for s, (a, b) in enumerate(pairs)}
+            if rank == 0 else None,
+            'pool_skipped_expansions': stats.get('pool_skipped_expansions')}
+
+
+# ------------------------------------------------- BASELINE.json configs[0] --
+
+class UniformStubNet:
+    """The evaluator plug-in of BASELINE.md section 3: value 0, uniform
+    moves_logprob over the legal moves (padding -99, network.py:150), with the
+    interface the search calls (mcts.py:203-210)."""
+
+    def __init__(self):
+        import torch
+        self.device = torch.device('cpu')
+
+    def eval(self):
+        return self
+
+    def run(self, batch):
+        import torch
+        legal = batch['legal_moves']
+        logit = torch.where(legal > 0, torch.zeros(legal.shape), torch.full(legal.shape, -99.0))
+        return {'value': torch.zeros(len(legal)), 'moves_logprob': torch.log_softmax(logit, dim=1)}
+
+
+def bench_config1(dev):
+    """The single-game drop-in (AzaleaAgent.choose_action / execute_action on a
+    1-game engine, evaluator called on the host exactly as the reference calls
+    it): latency per move of BASELINE.json config 1, to put beside the
+    reference's 0.16-0.25 s/move."""
+    import azalea_b200 as az
+    p = az.Policy()
+    p.net = UniformStubNet()
+    p.simulations, p.search_batch_size = SEARCH['simulations'], SEARCH['search_batch_size']
+    p.exploration_coef, p.exploration_depth = SEARCH['exploration_coef'], SEARCH['exploration_depth']
+    p.exploration_noise_alpha = SEARCH['exploration_noise_alpha']
+    p.exploration_noise_scale = SEARCH['exploration_noise_scale']
+    p.exploration_temperature = SEARCH['exploration_temperature']
+    agent = az.AzaleaAgent(lambda: az.HexGame(11), policy=p)
+    agent.settings['move_sampling'] = True
+    agent.settings['move_exploration'] = True
+    agent.reset()
+    agent.seed(1)
+    for _ in range(2):
+        agent.execute_action(agent.choose_action())
+    t0 = time.perf_counter()
+    moves = 0
+    while moves < 20 and not agent.game.state.result:
+        agent.execute_action(agent.choose_action())
+        moves += 1
+    secs = time.perf_counter() - t0
+    per_move = (SEARCH['simulations'] // SEARCH['search_batch_size'] + 1) * SEARCH['search_batch_size']
+    out = {'workload': 'Hex 11x11 single game through AzaleaAgent/Policy (drop-in API), uniform stub '
+                       'evaluator on the host, 800 sims batch 10, self-play settings',
+           'moves': moves, 's_per_move': secs / moves, 'moves_per_sec': moves / secs,
+           'value': per_move * moves / secs, 'unit': UNIT,
+           'host_copies_per_search_batch': {'d2h': 1, 'h2d': 1, 'syncs': 1}}
+    out.update(reference_python_figures())
+    return out
 
 
 def sp_launches(args, per_move, evaluator=None):
@@ -554,9 +874,11 @@ def sp_launches(args, per_move, evaluator=None):
     if args.evaluator == 'stub':
         per += nb + 1
     else:
-        own = 2
+        own = 2                 # stem, heads
         if getattr(evaluator, 'tower', None) == 'tcgen05':
-            own += 2 * len(evaluator.resblocks)
+            own += 1            # tail
+            fused = getattr(evaluator, 'tower_fused', False) and evaluator._fast.get('tower_fused')
+            own += (1 if fused else 2) * len(evaluator.resblocks)
         per += (nb + 1) * own
     return per
 

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define AZ_ABI_VERSION 1
+#define AZ_ABI_VERSION 2
 
 enum {
     AZ_OK = 0,
@@ -72,7 +72,20 @@ typedef struct az_config {
     int64_t first_game_id;   /* global id of local game 0 (rank * G) */
     int64_t game_id_stride;  /* ids of successive games in one slot differ by this
                                 (total games over all ranks) */
+    int32_t flags;           /* AZ_CFG_* */
+    int32_t reserved;
 } az_config;
+
+/* az_config.flags */
+enum {
+    /* When a game's physical node pool is exhausted, leave the leaf
+     * unexpanded (it is still backed up, and expanded on a later visit once
+     * the next re-root has compacted the pool) instead of flagging
+     * AZ_ST_POOL_FULL and dropping the game.  The reference never gets there
+     * (one 1e7-node pool per game, search_tree.py:17-18); skipped expansions
+     * are counted in AZ_CNT_POOL_SKIPPED. */
+    AZ_CFG_SOFT_POOL_FULL = 1
+};
 
 typedef struct az_engine az_engine;
 
@@ -104,7 +117,9 @@ enum {
     AZ_CNT_REPLAY_DROPPED = 8,
     AZ_CNT_GAMES_FAILED = 9,  /* dropped on SearchTreeFull, parallel_player.py:71-76 */
     AZ_CNT_COMPACTED_NODES = 10,
-    AZ_CNT_NN_ROWS = 11       /* non-terminal unique leaves (rows the network must evaluate) */
+    AZ_CNT_NN_ROWS = 11,      /* non-terminal unique leaves (rows the network must evaluate) */
+    AZ_CNT_POOL_SKIPPED = 12, /* expansions skipped because the pool half was full (AZ_CFG_SOFT_POOL_FULL) */
+    AZ_CNT_TERMINAL_LEAVES = 13 /* unique leaves that were terminal positions (value -1, mcts.py:192-195) */
 };
 
 typedef struct az_buffer_desc {
@@ -265,6 +280,19 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size,
 int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev,
                 const float *b_dev, void *out_dev, int64_t out_board_stride,
                 int channels, int heads, int padded_board_size, void *stream);
+
+/* Everything after the merged fully connected GEMM (network.py:78-80,145): y
+ * bf16 [num_boards][ld] holds, WITHOUT bias, the value_fc2 pre-activations in
+ * columns [0, nfc2) and the move_fc logits over tiles in [nfc2, nfc2 + n*n);
+ * fc_bias f32 [>= nfc2 + n*n], w3 f32 [nfc2] and b3 f32 [1] = value_fc3.
+ * value[b * value_stride] = tanh(w3 . relu(y[:nfc2] + bias) + b3) and
+ * logits[b * logits_stride + tile] = y + bias, both fp32 and both nullable --
+ * pass the engine's AZ_BUF_VALUE / AZ_BUF_PRIOR rows to hand the evaluation to
+ * az_mcts_expand_backup(.., AZ_PRIOR_LOGITS) without any copy. */
+int az_nn_tail(const void *y_dev, int64_t num_boards, int ld, int nfc2,
+               int board_size, const float *fc_bias_dev, const float *w3_dev,
+               const float *b3_dev, float *value_dev, int64_t value_stride,
+               float *logits_dev, int64_t logits_stride, void *stream);
 
 /* One tower convolution (Resblock.conv1/conv2 + BatchNorm + ReLU, with the
  * residual add for conv2; network.py:17-39) as a tcgen05 implicit GEMM, 64 ->

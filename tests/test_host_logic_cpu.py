@@ -189,3 +189,71 @@ def test_policy_trainer_config_helpers():
     assert pt._game_class('hex') is HexGame
     assert pt._game_class('azalea.game.hex.HexGame') is HexGame
     assert pt._game_class('azalea_b200.game.hex.HexGame') is HexGame
+
+
+class _FakeAgent:
+    """An agent as far as evaluate() looks at one: .policy and .game.board_size."""
+
+    class _Game:
+        board_size = 5
+
+    def __init__(self, tag):
+        self.policy = tag
+        self.game = self._Game()
+
+
+def _fake_play(first, second, board_size, seed=0, device=None, game_ids=None, stats=None, **kw):
+    """Stands in for play_matches on a GPU-less box: a game's result is a
+    function of its global task id and of who moves first, nothing else."""
+    res = [3 if (7 * gid + 3 * first[i] + second[i] + seed) % 3 else 1
+           for i, gid in enumerate(game_ids)]
+    return np.array(res, dtype=np.int64), np.zeros((0, len(res)), dtype=np.int32)
+
+
+def _tournament_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from azalea_b200.evaluation import evaluate
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}',
+                            rank=rank, world_size=world)
+    agents = [_FakeAgent(i) for i in range(5)]
+    out = evaluate(agents, 7, _play=_fake_play)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tournament_sharding_and_reduce_two_ranks_gloo():
+    """evaluate() under torch.distributed: (round, pair) tasks go round-robin
+    to the ranks (evaluation.py:49-58 fans them over worker processes), the
+    [pairs, 3] tallies are reduced onto rank 0, and the result equals the
+    single-process tournament."""
+    import torch.multiprocessing as mp
+    from azalea_b200.evaluation import evaluate, gen_pairs, tournament_tasks
+    agents = [_FakeAgent(i) for i in range(5)]
+    whole = evaluate(agents, 7, _play=_fake_play)
+    assert sorted(whole) == sorted(gen_pairs(5)) and len(whole) == 10
+    assert all(sum(v) == 7 for v in whole.values())
+    # the shares partition the task list, in the reference's order
+    t0, t1 = tournament_tasks(5, 7, 0, 2), tournament_tasks(5, 7, 1, 2)
+    assert sorted(t[0] for t in t0 + t1) == list(range(70))
+    assert all(t[0] % 2 == 0 for t in t0) and all(t[0] % 2 == 1 for t in t1)
+    for t, r, s, pair, order in t0 + t1:
+        assert t == r * 10 + s and pair == gen_pairs(5)[s]
+        assert order == np.random.RandomState(10000 * r + s).choice([-1, 1])
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tournament_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0] == whole                      # rank 0: the whole tournament
+    share1 = evaluate(agents, 7, rank=1, world_size=2, reduce=False, _play=_fake_play)
+    assert got[1] == share1                     # rank 1 keeps its own share
+    assert sum(sum(v) for v in share1.values()) == 35

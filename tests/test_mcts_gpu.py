@@ -349,3 +349,46 @@ def test_deep_search_19x19_vs_oracle():
         eng.tree_move(move_ids)
         eng.hex_step(moves)
     assert nodes.max() > 3_000_000
+
+
+@pytest.mark.parametrize('name', ('rough7_run', 'dyadic11_run'))
+def test_play_game_reproduces_reference_game(golden_mcts, name):
+    """azalea_b200.play_game (azalea/play_game.py:18-78) with one self-play
+    agent on both sides, as policy_trainer.py:72-75 plays it: the moves, the
+    result, the recorded states / move distributions and the alternating
+    rewards (play_game.py:63-67) are those of the reference's game."""
+    import azalea_b200 as az
+    g = golden_mcts
+    n, sims, batch, mode, seed, sampling, depth = (int(x) for x in g[f'{name}/config'])
+    moves = [int(m) for m in g[f'{name}/move']]
+    agent = make_agent(n, sims, batch, float(g[f'{name}/coef']), mode, depth)
+    agent.seed(seed)
+    agent.settings['move_sampling'] = bool(sampling)
+    whole = int(g[f'{name}/result']) != 0       # the trace is a finished game
+    result, data, metrics = az.play_game([agent], collect_data=True,
+                                         game_max_length=300 if whole else len(moves))
+    assert len(data) == len(moves)
+    board = np.zeros((n, n), dtype=np.int32)
+    for ply, rec_move in enumerate(moves):
+        st = data.state[ply]
+        assert st.color == ply % 2 and st.result == 0
+        assert (st.board == board).all(), ply
+        k = int(g[f'{name}/k'][ply])
+        assert len(st.legal_moves) == k
+        want = g[f'{name}/probs'][ply][:k].astype(np.float32)
+        assert data.moves_prob[ply].dtype == np.float32
+        assert data.moves_prob[ply].tobytes() == want.tobytes(), ply
+        board.flat[rec_move - 1] = 1 + ply % 2
+    if whole:
+        assert result == int(g[f'{name}/result'])
+        assert (agent.game.state.board == board).all()
+    else:
+        assert result == 2                      # game_max_length reached: a draw (play_game.py:57-61)
+    want_reward = np.full(len(moves), result - 2.0, dtype=np.float32)
+    want_reward[1::2] *= -1
+    assert np.array_equal(np.asarray(data.reward, dtype=np.float32), want_reward)
+    assert metrics['moves_per_game'] == len(moves) and metrics['games'] == 1
+    assert metrics['reward'] == float(want_reward[-1])
+    nodes = np.asarray(g[f'{name}/num_nodes'], dtype=np.float64)
+    assert np.isclose(metrics['search_tree_nodes'], nodes.mean())
+    assert np.isclose(metrics['search_value'], np.mean(g[f'{name}/search_value']), atol=1e-5)

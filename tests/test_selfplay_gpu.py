@@ -594,3 +594,67 @@ def test_windowed_streams_do_not_change_the_games(streams):
         assert np.array_equal(c1, c2)
         assert r1.shape == r2.shape and np.array_equal(r1, r2)
         assert n1 == n2
+
+
+@pytest.mark.parametrize('temperature', (1.0, 0.5))
+def test_play_commit_samples_the_visit_distribution(temperature):
+    """k_play_commit's move draw (policy.py:160 multinomial over
+    as_distribution(visits, T), search_tree.py:327-344) on the device Philox
+    streams: 4096 games at the same position have the same root visit counts
+    N and independent streams, so the chosen moves must be a sample of
+    p ~ N^(1/T): chi-square against the exact distribution, and never an
+    unvisited child."""
+    from azalea_b200 import Engine
+    from azalea_b200.search_tree import as_distribution
+    G, n, sims, batch = 4096, 5, 60, 6
+    eng = Engine(G, n, max_batch=batch, seed=1234)
+    eng.select_root()
+    eng.stub_eval(stubs.ROUGH)
+    eng.expand_root()
+    for _ in range(sims // batch + 1):
+        eng.select(batch, 0.5)
+        eng.stub_eval(stubs.ROUGH)
+        eng.expand_backup()
+    v, _, _, k, _, _ = (x.cpu().numpy() for x in eng.root_stats())
+    assert (k == n * n).all() and (v == v[0]).all()     # identical trees
+    chosen = torch.zeros(G, 4, dtype=torch.int32, device=eng.device)
+    eng.play_commit(temperature, 15, True, False, False, chosen)
+    move_id = chosen[:, 1].cpu().numpy()
+    p = as_distribution(v[0], temperature)
+    obs = np.bincount(move_id, minlength=n * n).astype(np.float64)
+    assert obs[p == 0].sum() == 0
+    live = p > 0
+    assert live.sum() >= 8
+    chi2 = float((((obs - G * p) ** 2)[live] / (G * p[live])).sum())
+    dof = int(live.sum()) - 1
+    # P(chi2_dof > dof + 5 sqrt(2 dof)) < 1e-5; the streams are fixed, so this
+    # either always passes or always fails
+    assert chi2 < dof + 5 * np.sqrt(2 * dof), (chi2, dof)
+    # and the games did not all draw the same number
+    assert len(np.unique(move_id)) >= 5
+
+
+def test_play_commit_temperature_zero_is_uniform_over_the_ties():
+    """Temperature 0 (search_tree.py:338-339): uniform over the arg-max ties."""
+    from azalea_b200 import Engine
+    G, n = 2048, 5
+    eng = Engine(G, n, max_batch=4, seed=99)
+    eng.select_root()
+    eng.stub_eval(stubs.UNIFORM)
+    eng.expand_root()
+    for _ in range(9):              # 36 descents over 25 children: visits 2 / 1
+        eng.select(4, 0.5)
+        eng.stub_eval(stubs.UNIFORM)
+        eng.expand_backup()
+    v = eng.root_stats()[0].cpu().numpy()
+    top = np.flatnonzero(v[0] == v[0].max())
+    assert 1 < len(top) < n * n
+    chosen = torch.zeros(G, 4, dtype=torch.int32, device=eng.device)
+    eng.play_commit(1.0, 0, True, False, False, chosen)     # ply 0 >= depth 0: T = 0
+    move_id = chosen[:, 1].cpu().numpy()
+    assert set(move_id) <= set(top)
+    obs = np.bincount(move_id, minlength=n * n)[top].astype(np.float64)
+    exp = G / len(top)
+    chi2 = float(((obs - exp) ** 2 / exp).sum())
+    dof = len(top) - 1
+    assert chi2 < dof + 5 * np.sqrt(2 * dof), (chi2, dof)

@@ -1,0 +1,478 @@
+// az_block.cuh -- one residual block of the evaluator's tower in ONE launch (sm_100a):
+//     x <- relu(conv2(relu(conv1(x) + b1)) + b2 + x)         (network.py:17-39, BN folded)
+// on tcgen05 tensor cores, in place, reading x once and writing it once.
+//
+// az_tower.cuh runs a block as two launches, x -> y and y, x -> x: five passes over the
+// activations per block (2 + 3), and in the power-capped steady state of the self-play step
+// both launches sit on the HBM roofline (4.5 TB/s sustained, profiles/r01_*).  The
+// intermediate y never needs to exist in memory.  What stands in the way of fusing the two
+// convolutions on one SM is shared memory and TMEM: both layers' weights are 144 KB, and
+// two accumulator rings of four blocks would split half of the N = 192 MMA windows at the
+// ring end (+46 cycles per pair, tools/probe/umma_gap.cu).
+//
+// So the block runs on a CLUSTER OF TWO CTAs, a producer and a consumer, each a complete
+// k_conv3x3 pipeline with its own layer's weights (72 KB) and its own full eight-block TMEM
+// ring (every MMA window stays N = 192, cta_group::1, no split):
+//
+//   CTA 0 "P" (conv1):  x slabs --bulk g2s--> input ring --MMA--> TMEM --epilogue(+b1, ReLU)-->
+//                       staging tile --cp.async.bulk shared::cta -> shared::cluster--> C's input ring
+//   CTA 1 "C" (conv2):  y slabs arrive in its input ring straight from P's shared memory
+//                       (distributed shared memory, complete_tx on C's own mbarrier) --MMA-->
+//                       TMEM --epilogue(+b2, + x from a bulk-loaded residual ring, ReLU)-->
+//                       staging tile --bulk s2g--> x (in place)
+//
+// The residual x slab is read a second time by C a few microseconds after P read it: an L2
+// hit (126 MB L2, the whole device has ~10 MB of slabs in flight).  HBM traffic per block is
+// one read and one write of the activations (2 units instead of 5), and the kernel is bound
+// by the tensor pipe: every SM issues 12 back-to-back 128x192x16 MMAs per slab.
+//
+// Flow control between the two CTAs (all mbarriers, no spinning on memory):
+//   C.in_full[st]    tx barrier of y-ring stage st; armed by C (arrive.expect_tx), completed by
+//                    the bytes of P's shared-to-shared bulk copy
+//   P.y_free[st]     remote arrive by C once MMA2 of the slab in stage st has retired
+//   P.out_empty[sb]  remote arrive by C once the slab copied from P's staging tile sb has
+//                    landed (the copy completes on C's barrier only, so C tells P)
+// No tile ever mixes bulk writes with bulk reads (staging: generic writes + bulk reads;
+// input / residual rings: bulk writes + tensor-core / generic reads).
+//
+// Everything else -- slab layout, pointer-shift taps, dy stacking into a TMEM accumulator
+// ring, ping-pong MMA issuers, two epilogue groups -- is az_tower.cuh's; see there.
+//
+// Roles (704 threads per CTA):
+//   warps 0-15   epilogue (two groups of eight on alternate output slabs)
+//   warps 16,17  MMA issuers (even / odd slabs)
+//   warp 18      loader: weights; P: x chunks (144 rows); C: residual slabs (128 rows)
+//   warp 19      C: relay a (slab landed -> P.out_empty)
+//   warp 20      storer: P: staging -> C's ring (DSMEM bulk copy); C: staging -> global
+//   warp 21      C: relay b (MMA2 retired -> re-arm in_full, P.y_free)
+#pragma once
+
+#include "az_tower.cuh"
+
+#define AZB_THREADS 704
+#ifndef AZB_SX
+#define AZB_SX 5   // P: input ring stages (x chunks)
+#endif
+#ifndef AZB_TP
+#define AZB_TP 3   // P: staging tiles
+#endif
+#ifndef AZB_SY
+#define AZB_SY 4   // C: input ring stages (y slabs from P)
+#endif
+#ifndef AZB_SR
+#define AZB_SR 3   // C: residual ring stages
+#endif
+#ifndef AZB_TC
+#define AZB_TC 2   // C: staging tiles
+#endif
+#ifndef AZB_PROF
+#define AZB_PROF 0          // probe build: wait-time breakdown per role into p.dbg_cnt
+#endif
+#if AZB_PROF
+#define AZB_T0() const long long t0_ = clock64()
+#define AZB_ACC(var) var += clock64() - t0_
+#else
+#define AZB_T0() do {} while (0)
+#define AZB_ACC(var) do {} while (0)
+#endif
+#define AZB_SMAX (AZB_SX > AZB_SY ? AZB_SX : AZB_SY)
+#define AZB_TMAX (AZB_TP > AZB_TC ? AZB_TP : AZB_TC)
+#define AZB_SMEM_P (AZT_WBYTES + AZB_SX * AZT_CHUNK_BYTES + AZB_TP * AZT_OUT_BYTES)
+#define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_SR + AZB_TC) * AZT_OUT_BYTES)
+#define AZB_SMEM_BYTES (AZB_SMEM_P > AZB_SMEM_C ? AZB_SMEM_P : AZB_SMEM_C)
+
+struct azb_params {
+    uint8_t *x;             // activations, slab layout, pre-swizzled; updated in place
+    const uint8_t *w;       // [2 layers][3 dx][192 = dy*64 + c_out][128 B] pre-swizzled weights
+    const float *bias;      // [2][64]
+    int n;                  // board size
+    int bpg;                // boards per group = 128 / (n+1)
+    long long groups;       // board groups
+    uint8_t *dbg_y;         // probe only: P also writes its output slabs here (slab layout), or NULL
+    unsigned *dbg_cnt;      // probe only: [0] residual-ring chunks that differ from global memory
+};
+
+__device__ __forceinline__ uint32_t azb_cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+__device__ __forceinline__ void azb_cluster_sync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t azb_remote(const void *p, uint32_t rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(azt_smem(p)), "r"(rank));
+    return r;
+}
+
+__device__ __forceinline__ void azb_remote_arrive(uint32_t bar_cluster)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+
+// wait on an own barrier whose phase is completed from the other CTA (remote arrive, or the
+// bytes of a shared-to-shared bulk copy)
+__device__ __forceinline__ void azb_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(azt_smem(bar)), "r"(parity) : "memory");
+    }
+}
+
+// own shared memory -> the other CTA's shared memory; completes (complete_tx) on a barrier
+// of the destination CTA
+__device__ __forceinline__ void azb_bulk_s2s(uint32_t dst_cluster, const void *src, uint32_t bytes,
+                                             uint32_t bar_cluster)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_cluster), "r"(azt_smem(src)), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AZB_THREADS, 1)
+k_resblock(const azb_params p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t rank = azb_cluster_rank();
+    const bool isP = rank == 0;                                     // conv1 producer | conv2 consumer
+    uint8_t *s_w = smem;                                            // this CTA's layer, 72 KB
+    uint8_t *s_in = smem + AZT_WBYTES;                              // input ring: same offset in both CTAs
+    uint8_t *s_res = s_in + AZB_SY * AZT_CHUNK_BYTES;               // C: residual ring
+    uint8_t *s_out = isP ? s_in + AZB_SX * AZT_CHUNK_BYTES : s_res + AZB_SR * AZT_OUT_BYTES;
+    const int S = isP ? AZB_SX : AZB_SY, T = isP ? AZB_TP : AZB_TC;
+    __shared__ uint64_t bar_w, bar_in_full[AZB_SMAX];
+    __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7
+    __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
+    __shared__ uint64_t bar_out_empty[AZB_TMAX], bar_out_done[AZB_TMAX];
+    __shared__ uint64_t bar_res_full[AZB_SR], bar_res_empty[AZB_SR];        // C
+    __shared__ uint64_t bar_y_free[AZB_SY];                                 // P (arrived by C)
+    __shared__ uint32_t tmem_holder;
+    __shared__ __align__(16) float s_bias[AZT_C];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        azt_mbar_init(&bar_w, 1);
+        for (int i = 0; i < AZB_SMAX; i++) azt_mbar_init(&bar_in_full[i], 1);
+        for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
+        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
+        for (int i = 0; i < AZB_TMAX; i++) {
+            azt_mbar_init(&bar_out_empty[i], 1);        // P: relay a of C; C: the storer
+            azt_mbar_init(&bar_out_done[i], 8);         // one arrival per warp of the group that wrote the slab
+        }
+        for (int i = 0; i < AZB_SR; i++) {
+            azt_mbar_init(&bar_res_full[i], 1);
+            azt_mbar_init(&bar_res_empty[i], 8);        // the eight warps of the group that read it
+        }
+        for (int i = 0; i < AZB_SY; i++) azt_mbar_init(&bar_y_free[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+        // C arms every stage of its input ring for the first slab P will copy into it
+        if (!isP)
+            for (int i = 0; i < AZB_SY; i++) azt_mbar_expect_tx(&bar_in_full[i], AZT_OUT_BYTES);
+    }
+    if (tid < AZT_C) s_bias[tid] = p.bias[rank * AZT_C + tid];
+    if (!isP) {
+        // P only ever writes the 128 slab rows of a stage; the 8 rows in front of them are the
+        // zero rows every slab is preceded by, the 8 rows behind feed masked outputs only
+        for (int i = tid; i < AZB_SY * AZT_CHUNK_BYTES / 16; i += AZB_THREADS)
+            reinterpret_cast<uint4 *>(s_in)[i] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(azt_smem(&tmem_holder)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_holder;
+
+    // this cluster's contiguous range of groups -> slabs [q0, q0 + nslabs), local index j = q - q0;
+    // board row y = j % n
+    const int n = p.n;
+    const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+    const long long g0 = p.groups * cid / ncl, g1 = p.groups * (cid + 1) / ncl;
+    const long long q0 = g0 * n;
+    const int nslabs = (int)((g1 - g0) * n);
+#define AZB_RING(u) ((8 - ((u) & 7)) & 7)
+
+    if (warp < 16) {
+        // zero the whole accumulator ring once: every MMA accumulates
+        const uint32_t tq = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int c = (warp >> 2) * 16; c < 512; c += 64) azt_tmem_zero16(tq + c);
+        asm volatile("tcgen05.wait::st.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // both CTAs' barriers are initialised (and C's ring armed) before either touches the other's
+    azb_cluster_sync();
+
+    if (warp == 21) {
+        // ------------------------------------------------------- relay b (C) --
+        if (!isP && lane == 0) {
+            for (int j = 0; j < nslabs; j++) {
+                const int st = j % AZB_SY;
+                azt_mbar_wait(&bar_mma_done[j & 7], (j >> 3) & 1);
+                // MMA2(j) has read stage st: arm it for its next slab, then let P copy that slab in
+                if (j + AZB_SY < nslabs) {
+                    azt_mbar_expect_tx(&bar_in_full[st], AZT_OUT_BYTES);
+                    azb_remote_arrive(azb_remote(&bar_y_free[st], 0));
+                }
+            }
+        }
+    } else if (warp == 20) {
+        // ------------------------------------------------------------ storer --
+        if (lane == 0 && isP) {
+            // finished y slab: staging tile -> rows 8..135 of stage st of C's input ring
+            for (int j = 0; j < nslabs; j++) {
+                const int sb = j % AZB_TP, st = j % AZB_SY;
+                azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1);
+                if (j >= AZB_SY) azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1);
+                if (p.dbg_y) {
+                    azt_bulk_s2g(p.dbg_y + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
+                                 AZT_OUT_BYTES);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                azb_bulk_s2s(azb_remote(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, 1),
+                             s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES, azb_remote(&bar_in_full[st], 1));
+            }
+            if (p.dbg_y) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else if (lane == 0) {
+            for (int j = 0; j < nslabs; j++) {
+                const int sb = j % AZB_TC;
+                azt_mbar_wait(&bar_out_done[sb], (j / AZB_TC) & 1);
+                azt_bulk_s2g(p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
+                             AZT_OUT_BYTES);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // hand the tile back as soon as the store has READ it (the write to global
+                // memory goes on): with two tiles the two epilogue groups must not wait for
+                // each other's stores to be issued
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                azt_mbar_arrive(&bar_out_empty[sb]);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp == 19) {
+        // ------------------------------------------------------- relay a (C) --
+        if (!isP && lane == 0) {
+            for (int j = 0; j < nslabs; j++) {
+                // slab j has landed in C: P's staging tile that held it may be rewritten
+                azb_wait_cluster(&bar_in_full[j % AZB_SY], (j / AZB_SY) & 1);
+                azb_remote_arrive(azb_remote(&bar_out_empty[j % AZB_TP], 0));
+            }
+        }
+    } else if (warp == 18) {
+        // ------------------------------------------------------------ loader --
+        if (lane == 0) {
+            azt_mbar_expect_tx(&bar_w, AZT_WBYTES);
+            const uint8_t *w = p.w + (size_t)rank * AZT_WBYTES;
+            for (int t = 0; t < 9; t++) azt_bulk_g2s(s_w + t * 8192, w + t * 8192, 8192, &bar_w);
+            if (isP) {
+                for (int j = 0; j < nslabs; j++) {
+                    const int st = j % AZB_SX;
+                    // the stage is free once the MMAs of the slab that used it last have retired
+                    if (j >= AZB_SX) azt_mbar_wait(&bar_mma_done[(j - AZB_SX) & 7], ((j - AZB_SX) >> 3) & 1);
+                    // slab rows plus 8 rows on each side: global rows [128 q, 128 q + 144)
+                    azt_mbar_expect_tx(&bar_in_full[st], AZT_CHUNK_BYTES);
+                    azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES, p.x + (size_t)((q0 + j) * 128) * AZT_ROW,
+                                 AZT_CHUNK_BYTES, &bar_in_full[st]);
+                }
+            } else {
+                // the residual: the block's own input slab, again (L2: P has just read it)
+                for (int j = 0; j < nslabs; j++) {
+                    const int sr = j % AZB_SR;
+                    azt_mbar_wait(&bar_res_empty[sr], ((j / AZB_SR) & 1) ^ 1);
+                    azt_mbar_expect_tx(&bar_res_full[sr], AZT_OUT_BYTES);
+                    azt_bulk_g2s(s_res + sr * AZT_OUT_BYTES, p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW,
+                                 AZT_OUT_BYTES, &bar_res_full[sr]);
+                }
+            }
+        }
+    } else if (warp >= 16) {
+        // -------------------------------------------------- MMA issuers --
+        // Warp 16 issues the even slabs, warp 17 the odd ones (az_tower.cuh).  The turn passes
+        // through named barriers 3 (-> even) and 4 (-> odd).
+        const int w = warp - 16;
+        azt_mbar_wait(&bar_w, 0);
+        const uint64_t db_base = azt_desc(azt_smem(s_w));
+        if (w == 1 && nslabs > 0) asm volatile("bar.arrive 3, 64;" ::: "memory");   // slab 0 has the first turn
+        for (int j = w, y = w % n; j < nslabs; j += 2, y = (y + 2) % n) {
+            const int st = j % S;
+            // input slab j feeds output slabs j+1 (dy 0), j (dy 1), j-1 (dy 2) of the same group
+            const int dy0 = y + 1 < n ? 0 : 1, dy1 = y > 0 ? 2 : 1;
+            const int top = j + 1 - dy0;
+            // highest output slab entered by the slabs before this one
+            const int entered = j == 0 ? -1 : (y == 0 ? j - 1 : j);
+            azb_wait_cluster(&bar_in_full[st], (j / S) & 1);
+            // a block entered for a new output slab t: its previous tenant t-8 must have been retired
+            for (int t = entered + 1; t <= top; t++)
+                if (t >= 8) azt_mbar_wait(&bar_blk_free[AZB_RING(t)], ((t >> 3) - 1) & 1);
+            const int blk = AZB_RING(top), nb = dy1 - dy0 + 1;
+            const int first = nb < 8 - blk ? nb : 8 - blk, second = nb - first;     // split where the ring wraps
+            const uint32_t d0 = tmem + blk * 64, i0 = AZT_IDESC(first), i1 = AZT_IDESC(second);
+            // descriptors advance in 16-byte units: one row = 8, one K step (32 B) = 2
+            const uint64_t da0 = azt_desc(azt_smem(s_in + st * AZT_CHUNK_BYTES) + 7 * AZT_ROW);    // row l-1 of the slab
+            const uint64_t db0 = db_base + (uint64_t)(dy0 * 64 * (AZT_ROW / 16));
+            const uint64_t db1 = db0 + (uint64_t)(first * 64 * (AZT_ROW / 16));
+            // take the turn: the other warp has issued slab j-1
+            if (w == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
+            else asm volatile("bar.sync 4, 64;" ::: "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (azt_elect()) {
+                if (second == 0) {
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
+                } else {
+                    // one accumulator range after the other (tools/probe/umma_gap.cu)
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            azt_mma(d0, da0 + (dx * 8 + k * 2), db0 + (dx * 192 * 8 + k * 2), i0);
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++)
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                            azt_mma(tmem, da0 + (dx * 8 + k * 2), db1 + (dx * 192 * 8 + k * 2), i1);
+                }
+                // one commit per slab: output slabs wait for it, and so does the input stage
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             ::"r"(azt_smem(&bar_mma_done[j & 7])) : "memory");
+            }
+            __syncwarp();
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            if (j + 1 < nslabs) {
+                if (w == 0) asm volatile("bar.arrive 4, 64;" ::: "memory");
+                else asm volatile("bar.arrive 3, 64;" ::: "memory");
+            }
+        }
+    } else {
+        // ----------------------------------------------------- epilogue --
+        // group = warp >> 3 takes the output slabs j = group (mod 2); inside a group a warp
+        // owns 32 channels (half) of the 32 rows its TMEM lane quadrant holds:
+        // thread = TMEM lane = row l of the slab
+        const int grp = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
+        const int l = wq * 32 + lane;
+        const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
+        const uint32_t keep = real ? 0xffffffffu : 0u;
+        const int sw = l & 7;                                       // == R & 7 (8 + 128 q + l)
+        for (int j = grp, y = grp % n; j < nslabs; j += 2, y = (y + 2) % n) {
+            const int sb = j % T;
+            uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
+            uint4 rv[4];
+            if (!isP) {
+                // this thread's row and channels of the residual slab, from the bulk-loaded ring
+                const int sr = j % AZB_SR;
+                azt_mbar_wait(&bar_res_full[sr], (j / AZB_SR) & 1);
+                const uint4 *rrow = reinterpret_cast<const uint4 *>(s_res + sr * AZT_OUT_BYTES + l * AZT_ROW);
+#pragma unroll
+                for (int c = 0; c < 4; c++) rv[c] = rrow[(half * 4 + c) ^ sw];
+                // The release below hands the stage to the NEXT BULK LOAD (async proxy).  An
+                // mbarrier arrive does not wait for the shared-memory loads issued before it:
+                // without this the arrive overtook them and slow warps read the slab that was
+                // loaded three slabs later (tools/probe/block_diag2.py found exactly that, in
+                // ~2 % of the rows).  Consuming the loaded registers in a warp vote makes every
+                // lane's loads return before lane 0 can arrive.  (fence.proxy.async here is the
+                // other cure and costs 4 %; __threadfence_block is not one.)
+                if (__any_sync(0xffffffffu, (rv[0].x ^ rv[1].y ^ rv[2].z ^ rv[3].w) == 0x7fc1a55eu &&
+                                                (rv[0].y ^ rv[1].x) == 0x5ea1c0deu && rv[2].x == 0xfeedbeefu))
+                    asm volatile("nanosleep.u32 1;");
+                __syncwarp();
+                if (lane == 0) azt_mbar_arrive(&bar_res_empty[sr]);
+                if (p.dbg_cnt) {
+                    // probe: the same chunks straight from global memory win, mismatches are counted
+                    const uint4 *grow = reinterpret_cast<const uint4 *>(
+                        p.x + (size_t)(AZT_HALO + (q0 + j) * 128 + l) * AZT_ROW);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const uint4 gv = grow[(half * 4 + c) ^ sw];
+                        if (gv.x != rv[c].x || gv.y != rv[c].y || gv.z != rv[c].z || gv.w != rv[c].w) {
+                            const unsigned k = atomicAdd(p.dbg_cnt, 1u);
+                            if (k < 256) {      // record: where, and what the ring held
+                                unsigned *rec = p.dbg_cnt + 16 + 8 * k;
+                                rec[0] = (unsigned)(q0 + j); rec[1] = (unsigned)l; rec[2] = (unsigned)(half * 4 + c);
+                                rec[3] = (unsigned)j;
+                                rec[4] = rv[c].x; rec[5] = rv[c].y; rec[6] = rv[c].z; rec[7] = rv[c].w;
+                            }
+                        }
+                        rv[c] = gv;
+                    }
+                }
+            }
+            // the staging tile must have been drained by the copy / store that used it last
+            if (isP) azb_wait_cluster(&bar_out_empty[sb], ((j / T) & 1) ^ 1);
+            else azt_mbar_wait(&bar_out_empty[sb], ((j / T) & 1) ^ 1);
+            // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
+            const int last = y + 1 < n ? j + 1 : j;
+            azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const int blk = AZB_RING(j);
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u + (uint32_t)half * 32u;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t acc[16];
+                AZT_TMEM_LD16(acc, ta + h * 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                azt_tmem_zero16(ta + h * 16);       // retire: zero for the block's next output slab
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const int c8 = half * 4 + h * 2 + g;            // 8-channel chunk of the row
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8 + 4]);
+                    float f[8];
+                    f[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
+                    if (!isP) {
+                        const uint4 r = rv[h * 2 + g];
+                        const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            f[2 * q] += __uint_as_float(rw[q] << 16);
+                            f[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                        }
+                    }
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
+                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
+                    }
+                    srow[c8 ^ sw] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            }
+            // hand the ring block back
+            asm volatile("tcgen05.wait::st.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
+            // staging tile complete: the storer sends it on (async proxy reads it)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);
+        }
+    }
+#undef AZB_RING
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    // neither CTA may leave while the other can still reach into its shared memory
+    azb_cluster_sync();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
+}

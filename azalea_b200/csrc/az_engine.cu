@@ -12,6 +12,7 @@
 #include "az_kernels.cuh"
 #include "az_nn_glue.cuh"
 #include "az_tower.cuh"
+#include "az_block.cuh"
 
 static thread_local char g_cuda_err[256] = "";
 
@@ -1165,6 +1166,61 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev, c
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
     return azt_launch(p, resid_dev != nullptr, stream);
 }
+
+static int azb_max_clusters[AZ_MAX_DEVICES];
+
+int az_nn_resblock_clusters(void)
+{
+    /* diagnostic: clusters of two CTAs az_nn_resblock found resident at once on the current
+     * device (0 before its first launch there) */
+    return azb_max_clusters[az_current_device()];
+}
+
+static void *azb_dbg_y = nullptr;
+static unsigned *azb_dbg_cnt = nullptr;
+
+/* probe hook (tools/probe/block_diag.py; not part of the ABI): the next launches also write the
+ * intermediate slabs to y_dev and count residual-ring mismatches in cnt_dev (NULL, NULL = off) */
+void azb_set_debug(void *y_dev, unsigned *cnt_dev) { azb_dbg_y = y_dev; azb_dbg_cnt = cnt_dev; }
+
+int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, int board_size,
+                   int64_t num_boards, void *stream)
+{
+    if (!x_dev || !w_dev || !bias_dev || board_size < 2 || board_size > 19 || num_boards < 0)
+        return AZ_E_INVALID;
+    if (num_boards == 0) return AZ_OK;
+    azb_params p = {};
+    p.x = (uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
+    p.n = board_size; p.bpg = 128 / (board_size + 1);
+    p.groups = (num_boards + p.bpg - 1) / p.bpg;
+    p.dbg_y = (uint8_t *)azb_dbg_y; p.dbg_cnt = azb_dbg_cnt;
+    // clusters of two CTAs (one per SM) that can be resident at once on this device
+    int *max_clusters = azb_max_clusters;
+    const int dev = az_current_device();
+    if (max_clusters[dev] == 0) {
+        int rc = az_check(cudaFuncSetAttribute(k_resblock, cudaFuncAttributeMaxDynamicSharedMemorySize, AZB_SMEM_BYTES));
+        if (rc != AZ_OK) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (unsigned)(az_sm_count(dev) / 2));
+        cfg.blockDim = dim3(AZB_THREADS);
+        cfg.dynamicSmemBytes = AZB_SMEM_BYTES;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int nc = 0;
+        rc = az_check(cudaOccupancyMaxActiveClusters(&nc, k_resblock, &cfg));
+        if (rc != AZ_OK) return rc;
+        if (nc < 1) return AZ_E_UNSUPPORTED;
+        if (nc > az_sm_count(dev) / 2) nc = az_sm_count(dev) / 2;
+        max_clusters[dev] = nc;
+    }
+    const long long clusters = p.groups < max_clusters[dev] ? p.groups : max_clusters[dev];
+    k_resblock<<<(unsigned)(2 * clusters), AZB_THREADS, AZB_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+    return az_check(cudaGetLastError());
+}
+
+static_assert(AZB_SMEM_BYTES + 1024 <= 232448, "k_resblock: dynamic + static shared memory per CTA");
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)
 {

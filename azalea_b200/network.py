@@ -192,6 +192,10 @@ class HexNetwork(nn.Module):
                 return keep(pack_conv_weights(w.to(dev, dtype))), keep32(b)
             fast['tower'] = [(pack_tower(b.conv1, b.bn1), pack_tower(b.conv2, b.bn2))
                              for b in self.resblocks]
+            # the same, block by block, for the fused launch (csrc/az_block.cuh)
+            fast['tower_fused'] = [
+                (keep(torch.cat([w1, w2])), keep32(torch.cat([b1, b2])))
+                for (w1, b1), (w2, b2) in fast['tower']]
         fast['tower_buf'] = old['tower_buf'] if old is not None else {}
         # the two 1x1 head convolutions read the same activations: one conv;
         # the two first fully connected layers read its output: one GEMM over

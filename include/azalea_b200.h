@@ -314,6 +314,20 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev,
                   const void *resid_dev, void *out_dev, int board_size,
                   int64_t num_boards, void *stream);
 
+/* One whole residual block (network.py:17-39: conv1 + BN + ReLU, conv2 + BN,
+ * + x, ReLU) in ONE launch and in place, x <- relu(conv2(relu(conv1(x))) + x),
+ * reading the activations once and writing them once (csrc/az_block.cuh: a
+ * cluster of two CTAs, conv1 on one SM streaming its output slabs through
+ * distributed shared memory into conv2 on the other).  x: slab layout as for
+ * az_nn_conv3x3; w: the two layers' packed weights back to back
+ * [2][3 kx][3 ky][64][64] bf16; bias f32 [2][64].  Bit-identical to
+ * az_nn_conv3x3(x, w1, b1, NULL, y) followed by az_nn_conv3x3(y, w2, b2, x, x). */
+int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev,
+                   int board_size, int64_t num_boards, void *stream);
+/* Diagnostic: how many two-CTA clusters az_nn_resblock sizes its grid for on
+ * the current device (cudaOccupancyMaxActiveClusters; 74 on a B200), 0 before
+ * the first launch. */
+int az_nn_resblock_clusters(void);
 
 /* Test aid for the root exploration noise (mcts.py:126-131), which only has
  * statistical parity with RandomState.dirichlet: writes the Dirichlet(alpha)

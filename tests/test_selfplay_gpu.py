@@ -438,6 +438,84 @@ def test_tcgen05_conv3x3_matches_torch(n, N):
         assert rest == 0.0
 
 
+@pytest.mark.parametrize('n,N', ((11, 64), (11, 1029), (19, 9), (7, 91), (5, 1), (11, 4100),
+                                 (2, 1), (2, 300), (3, 33), (11, 1480), (13, 2000), (11, 40960)))
+def test_fused_resblock_equals_two_launches(n, N):
+    """az_nn_resblock (csrc/az_block.cuh: conv1 and conv2 of a residual block on
+    a cluster of two CTAs, the intermediate slabs handed over through
+    distributed shared memory) is the SAME arithmetic as two az_nn_conv3x3
+    launches -- same MMAs in the same order, same bf16 rounding of the
+    intermediate -- so the outputs are bit-identical; and both match
+    network.py:17-39 evaluated in fp32 within two bf16 roundings.  Two blocks
+    back to back (different weights), in place, as the tower runs them."""
+    import ctypes
+    import torch.nn.functional as F
+    from azalea_b200 import _cabi, tower_layout as tl
+    L = _cabi.lib()
+    torch.manual_seed(100 + n)
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    ws = [(torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16) for _ in range(4)]
+    bs = [torch.randn(64, device='cuda') * 0.1 for _ in range(4)]
+    wp = [tl.pack_conv_weights(w) for w in ws]
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    # two launches per block
+    xa, ya = tl.to_slabs(x), torch.zeros_like(tl.to_slabs(x))
+    for blk in range(2):
+        _cabi.check(L.az_nn_conv3x3(p(xa), p(wp[2 * blk]), p(bs[2 * blk]), None, p(ya), n, N, stream))
+        _cabi.check(L.az_nn_conv3x3(p(ya), p(wp[2 * blk + 1]), p(bs[2 * blk + 1]), p(xa), p(xa), n, N, stream))
+    # one launch per block
+    xb = tl.to_slabs(x)
+    for blk in range(2):
+        w12 = torch.cat([wp[2 * blk], wp[2 * blk + 1]]).contiguous()
+        b12 = torch.cat([bs[2 * blk], bs[2 * blk + 1]]).contiguous()
+        _cabi.check(L.az_nn_resblock(p(xb), p(w12), p(b12), n, N, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(xa.view(torch.int16), xb.view(torch.int16))
+    got, rest = tl.from_slabs(xb, n, N)
+    assert rest == 0.0
+    # fp32 reference with the intermediate rounded to bf16 where the kernels round it
+    t = x.permute(0, 3, 1, 2).float()
+    for blk in range(2):
+        y = F.relu(F.conv2d(t, ws[2 * blk].float(), bs[2 * blk], padding=1)).to(torch.bfloat16).float()
+        t = F.relu(F.conv2d(y, ws[2 * blk + 1].float(), bs[2 * blk + 1], padding=1) + t)
+        t = t.to(torch.bfloat16).float()
+    want = t.permute(0, 2, 3, 1)
+    assert ((got.float() - want).abs() <= want.abs() * 2 ** -7 + 2e-2).all()
+
+
+def test_fused_resblock_concurrent_streams():
+    """Two instances of the fused block running concurrently on two streams
+    (what LockstepSelfPlay(streams=2) does) on their own buffers: results
+    equal the single-stream ones.  (The two-launch kernel's first residual
+    variant died in exactly this situation)"""
+    import ctypes
+    from azalea_b200 import _cabi, tower_layout as tl
+    L = _cabi.lib()
+    n, N = 11, 10240
+    torch.manual_seed(7)
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    w12 = torch.cat([tl.pack_conv_weights((torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16))
+                     for _ in range(2)]).contiguous()
+    b12 = (torch.randn(128, device='cuda') * 0.1).contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    ref = tl.to_slabs(x)
+    st0 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    reps = 30
+    for _ in range(reps):
+        _cabi.check(L.az_nn_resblock(p(ref), p(w12), p(b12), n, N, st0))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    bufs = [tl.to_slabs(x) for _ in streams]
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        for s, b in zip(streams, bufs):
+            _cabi.check(L.az_nn_resblock(p(b), p(w12), p(b12), n, N, ctypes.c_void_p(s.cuda_stream)))
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b.view(torch.int16), ref.view(torch.int16))
+
+
 def test_tcgen05_tower_matches_cudnn_tower():
     """The whole evaluator with the tcgen05 tower (AZALEA_B200_TOWER=tcgen05)
     against the default cuDNN tower on the same weights: both are bf16 with

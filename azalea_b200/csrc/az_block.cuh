@@ -5,81 +5,99 @@
 // az_tower.cuh runs a block as two launches, x -> y and y, x -> x: five passes over the
 // activations per block (2 + 3), and in the power-capped steady state of the self-play step
 // both launches sit on the HBM roofline (4.5 TB/s sustained, profiles/r01_*).  The
-// intermediate y never needs to exist in memory.  What stands in the way of fusing the two
-// convolutions on one SM is shared memory and TMEM: both layers' weights are 144 KB, and
-// two accumulator rings of four blocks would split half of the N = 192 MMA windows at the
-// ring end (+46 cycles per pair, tools/probe/umma_gap.cu).
+// intermediate y never needs to exist in memory.  Two things stand in the way of fusing the
+// two convolutions on ONE SM: shared memory and TMEM (both layers' weights are 144 KB, and two
+// accumulator rings of four blocks would split half of the N = 192 MMA windows at the ring
+// end), and shared-memory BANDWIDTH: the 12 MMAs of a slab read 120 KB of operands (A 48 KB,
+// the 72 KB of weights every slab) against 128 B/clock, 940 of the slab's 1152 MMA cycles --
+// k_conv3x3's measured 1337 cycles per slab are exactly its 170 KB of shared-memory traffic
+// per slab (operands + 18 KB input + staging tile written and read back).
 //
-// So the block runs on a CLUSTER OF TWO CTAs, a producer and a consumer, each a complete
-// k_conv3x3 pipeline with its own layer's weights (72 KB) and its own full eight-block TMEM
-// ring (every MMA window stays N = 192, cta_group::1, no split):
+// So the block runs on a CLUSTER OF TWO CTAs, a producer and a consumer, each with its own
+// layer's weights (72 KB) and its own eight-block TMEM ring (every MMA window stays N = 192,
+// cta_group::1, no split):
 //
-//   CTA 0 "P" (conv1):  x slabs --bulk g2s--> input ring --MMA--> TMEM --epilogue(+b1, ReLU)-->
-//                       staging tile --cp.async.bulk shared::cta -> shared::cluster--> C's input ring
-//   CTA 1 "C" (conv2):  y slabs arrive in its input ring straight from P's shared memory
-//                       (distributed shared memory, complete_tx on C's own mbarrier) --MMA-->
-//                       TMEM --epilogue(+b2, + x from a bulk-loaded residual ring, ReLU)-->
-//                       staging tile --bulk s2g--> x (in place)
+//   CTA 0 "P" (conv1):  x slabs --bulk g2s--> input ring --MMA--> TMEM --epilogue (+b1, ReLU,
+//                       bf16)--> staging tile --cp.async.bulk shared::cta -> shared::cluster-->
+//                       C's input ring (distributed shared memory; the copy completes, with
+//                       complete_tx, on C's own mbarrier)
+//   CTA 1 "C" (conv2):  --MMA--> TMEM --epilogue (+b2, + x from a bulk-loaded residual ring,
+//                       ReLU)--> staging tile --bulk s2g--> x (in place).  The residual x slab
+//                       is read a second time by C a few microseconds after P read it: an L2
+//                       hit (126 MB L2, ~10 MB of slabs in flight on the device).
 //
-// The residual x slab is read a second time by C a few microseconds after P read it: an L2
-// hit (126 MB L2, the whole device has ~10 MB of slabs in flight).  HBM traffic per block is
-// one read and one write of the activations (2 units instead of 5), and the kernel is bound
-// by the tensor pipe: every SM issues 12 back-to-back 128x192x16 MMAs per slab.
+// HBM traffic per block is one read and one write of the activations (2 units instead of 5).
 //
-// Flow control between the two CTAs (all mbarriers, no spinning on memory):
-//   C.in_full[st]    tx barrier of y-ring stage st; armed by C (arrive.expect_tx), completed by
-//                    the bytes of P's shared-to-shared bulk copy
-//   P.y_free[st]     remote arrive by C once MMA2 of the slab in stage st has retired
-//   P.out_empty[sb]  remote arrive by C once the slab copied from P's staging tile sb has
-//                    landed (the copy completes on C's barrier only, so C tells P)
+// Flow control between the two CTAs (mbarriers only, no cluster-scope fence on any hot path):
+//   C.in_full[st]    tx barrier of stage st of C's ring; armed by C (arrive.expect_tx),
+//                    completed by the bytes of P's shared-to-shared bulk copy
+//   P.y_free[st]     remote arrive by C's relay once MMA2 of the slab in stage st has retired
+//   P.out_empty[sb]  remote arrive by C's relay once the slab copied from P's staging tile sb
+//                    has landed (the copy completes on C's barrier only, so C tells P)
+// The remote arrives are RELAXED: they publish no data (the stage / tile they release was read
+// by the tensor core or the copy engine, whose completion the relay has observed), and a
+// release at cluster scope costs ~1000 cycles here (measured, profiles/r02_fused_block.txt).
 // No tile ever mixes bulk writes with bulk reads (staging: generic writes + bulk reads;
-// input / residual rings: bulk writes + tensor-core / generic reads).
+// input rings: bulk writes + tensor-core reads).
+//
+// Two lessons are built in (profiles/r02_fused_block.txt has the measurements):
+//  * An mbarrier arrive does NOT wait for the shared-memory loads issued before it.  The
+//    residual ring's release overtook the epilogue's loads and slow warps read the slab that
+//    was loaded three slabs later (~2 % of the rows wrong, nondeterministic); the release now
+//    depends on the loaded registers.
+//  * Anything with release semantics at cluster scope (mbarrier.arrive.release.cluster, and
+//    fence.proxy.async over all state spaces) costs 1000-2000 cycles per call here, with or
+//    without outstanding stores.  A variant whose P epilogue stored y straight into C's ring
+//    (st.shared::cluster, fence, release arrive; C with register residuals and direct global
+//    stores) was bit-exact and took 0.92 ms per block; its direct, per-row global accesses in
+//    C's epilogue (32 different lines per warp instruction) alone cost 0.19 ms each way.
 //
 // Everything else -- slab layout, pointer-shift taps, dy stacking into a TMEM accumulator
 // ring, ping-pong MMA issuers, two epilogue groups -- is az_tower.cuh's; see there.
 //
-// Roles (704 threads per CTA):
+// Roles (672 threads per CTA):
 //   warps 0-15   epilogue (two groups of eight on alternate output slabs)
 //   warps 16,17  MMA issuers (even / odd slabs)
 //   warp 18      loader: weights; P: x chunks (144 rows); C: residual slabs (128 rows)
-//   warp 19      C: relay a (slab landed -> P.out_empty)
-//   warp 20      storer: P: staging -> C's ring (DSMEM bulk copy); C: staging -> global
-//   warp 21      C: relay b (MMA2 retired -> re-arm in_full, P.y_free)
+//   warp 19      C: relay (slab landed -> P.out_empty; MMA2 retired -> re-arm, P.y_free)
+//   warp 20      storer: P: staging tile -> C's ring; C: staging tile -> global memory
 #pragma once
 
 #include "az_tower.cuh"
 
-#define AZB_THREADS 704
+#define AZB_THREADS 672
+#ifndef AZB_P_ASYNC
+#define AZB_P_ASYNC 0       // 0: y goes through a staging tile and a shared-to-shared bulk copy;
+#endif                      // 1 (probe): P's epilogue sends it with st.async, registers -> C's ring:
+                            // bit-exact too, but 4 x STAS.128 per thread and slab at the ~20 B/clock
+                            // of the SM-to-SM link keep P's epilogue busy 2600 cycles per slab
+                            // (0.65 ms per block against 0.59)
 #ifndef AZB_SX
-#define AZB_SX 5   // P: input ring stages (x chunks)
+#define AZB_SX (AZB_P_ASYNC ? 8 : 5)    // P: input ring stages (x chunks, bulk loads)
 #endif
 #ifndef AZB_TP
-#define AZB_TP 3   // P: staging tiles
+#define AZB_TP 3            // P: staging tiles (bulk-copy variant only)
 #endif
 #ifndef AZB_SY
-#define AZB_SY 4   // C: input ring stages (y slabs from P)
+#define AZB_SY 4            // C: input ring stages (y slabs copied in by P)
 #endif
 #ifndef AZB_SR
-#define AZB_SR 3   // C: residual ring stages
+#define AZB_SR 3            // C: residual ring stages (x slabs, bulk loads)
 #endif
 #ifndef AZB_TC
-#define AZB_TC 2   // C: staging tiles
+#define AZB_TC 2            // C: staging tiles
 #endif
+#define AZB_TMAX (AZB_TP > AZB_TC ? AZB_TP : AZB_TC)
 #ifndef AZB_PROF
-#define AZB_PROF 0          // probe build: wait-time breakdown per role into p.dbg_cnt
-#endif
-#if AZB_PROF
-#define AZB_T0() const long long t0_ = clock64()
-#define AZB_ACC(var) var += clock64() - t0_
-#else
-#define AZB_T0() do {} while (0)
-#define AZB_ACC(var) do {} while (0)
+#define AZB_PROF 0          // 1: probe build with per-role cycle accounting (tools/probe/block_time.py)
 #endif
 #define AZB_SMAX (AZB_SX > AZB_SY ? AZB_SX : AZB_SY)
-#define AZB_TMAX (AZB_TP > AZB_TC ? AZB_TP : AZB_TC)
-#define AZB_SMEM_P (AZT_WBYTES + AZB_SX * AZT_CHUNK_BYTES + AZB_TP * AZT_OUT_BYTES)
+#define AZB_SMEM_P (AZT_WBYTES + AZB_SX * AZT_CHUNK_BYTES + (AZB_P_ASYNC ? 0 : AZB_TP) * AZT_OUT_BYTES)
 #define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_SR + AZB_TC) * AZT_OUT_BYTES)
 #define AZB_SMEM_BYTES (AZB_SMEM_P > AZB_SMEM_C ? AZB_SMEM_P : AZB_SMEM_C)
+static_assert(AZB_SX <= 8 && AZB_SY <= 8, "stage reuse is tracked through the 8 MMA-retired barriers");
+static_assert(AZB_TC % 2 == 0, "each epilogue group of C owns its staging tiles");
+static_assert(!AZB_P_ASYNC || AZB_SY % 2 == 0, "st.async variant: a stage of C's ring belongs to one epilogue group of P");
 
 struct azb_params {
     uint8_t *x;             // activations, slab layout, pre-swizzled; updated in place
@@ -88,8 +106,9 @@ struct azb_params {
     int n;                  // board size
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
-    uint8_t *dbg_y;         // probe only: P also writes its output slabs here (slab layout), or NULL
-    unsigned *dbg_cnt;      // probe only: [0] residual-ring chunks that differ from global memory
+    unsigned long long *prof;   // probe only: per-role wait cycles of cluster 0 ([rank][32]) or NULL
+    int debug;              // probe only (tools/probe/block_time.py): 2 = C skips its global stores,
+                            // 4 = C skips the residual loads, 8 = no MMAs
 };
 
 __device__ __forceinline__ uint32_t azb_cluster_rank()
@@ -112,22 +131,10 @@ __device__ __forceinline__ uint32_t azb_remote(const void *p, uint32_t rank)
     return r;
 }
 
+// Arrive on a barrier of the other CTA without publishing anything (see the header comment).
 __device__ __forceinline__ void azb_remote_arrive(uint32_t bar_cluster)
 {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
-}
-
-// wait on an own barrier whose phase is completed from the other CTA (remote arrive, or the
-// bytes of a shared-to-shared bulk copy)
-__device__ __forceinline__ void azb_wait_cluster(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done) : "r"(azt_smem(bar)), "r"(parity) : "memory");
-    }
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
 }
 
 // own shared memory -> the other CTA's shared memory; completes (complete_tx) on a barrier
@@ -140,6 +147,43 @@ __device__ __forceinline__ void azb_bulk_s2s(uint32_t dst_cluster, const void *s
         ::"r"(dst_cluster), "r"(azt_smem(src)), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 
+// 16 bytes from registers into the other CTA's shared memory, asynchronously; the bytes are
+// counted (complete_tx) on a barrier of the destination CTA, so the sender needs no fence
+__device__ __forceinline__ void azb_st_async(uint32_t dst_cluster, const uint4 &v, uint32_t bar_cluster)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
+}
+
+// wait on an own barrier whose phase is completed from the other CTA
+__device__ __forceinline__ void azb_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(azt_smem(bar)), "r"(parity) : "memory");
+    }
+}
+
+// one 32-byte sector of a row: 16-byte chunks lo | hi
+__device__ __forceinline__ void azb_stg_sector(void *p, const uint4 &lo, const uint4 &hi)
+{
+    asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};"
+                 ::"l"(p), "l"((unsigned long long)lo.x | ((unsigned long long)lo.y << 32)),
+                   "l"((unsigned long long)lo.z | ((unsigned long long)lo.w << 32)),
+                   "l"((unsigned long long)hi.x | ((unsigned long long)hi.y << 32)),
+                   "l"((unsigned long long)hi.z | ((unsigned long long)hi.w << 32)) : "memory");
+}
+
+// probe: accumulate the cycles spent in `stmt` into slot k of this CTA's profile row
+#define AZB_TIMED(k, stmt)                                                          \
+    do {                                                                            \
+        if (prof_on) { const long long t0_ = clock64(); stmt; prof_acc[k] += clock64() - t0_; } \
+        else { stmt; }                                                              \
+    } while (0)
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AZB_THREADS, 1)
 k_resblock(const azb_params p)
 {
@@ -149,31 +193,34 @@ k_resblock(const azb_params p)
     uint8_t *s_w = smem;                                            // this CTA's layer, 72 KB
     uint8_t *s_in = smem + AZT_WBYTES;                              // input ring: same offset in both CTAs
     uint8_t *s_res = s_in + AZB_SY * AZT_CHUNK_BYTES;               // C: residual ring
-    uint8_t *s_out = isP ? s_in + AZB_SX * AZT_CHUNK_BYTES : s_res + AZB_SR * AZT_OUT_BYTES;
+    uint8_t *s_out = isP ? s_in + AZB_SX * AZT_CHUNK_BYTES : s_res + AZB_SR * AZT_OUT_BYTES;   // staging tiles
     const int S = isP ? AZB_SX : AZB_SY, T = isP ? AZB_TP : AZB_TC;
     __shared__ uint64_t bar_w, bar_in_full[AZB_SMAX];
+    __shared__ uint64_t bar_out_empty[AZB_TMAX], bar_out_done[AZB_TMAX];    // staging tiles
+    __shared__ uint64_t bar_res_full[AZB_SR], bar_res_empty[AZB_SR];        // C: residual ring
     __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7
     __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
-    __shared__ uint64_t bar_out_empty[AZB_TMAX], bar_out_done[AZB_TMAX];
-    __shared__ uint64_t bar_res_full[AZB_SR], bar_res_empty[AZB_SR];        // C
-    __shared__ uint64_t bar_y_free[AZB_SY];                                 // P (arrived by C)
+    __shared__ uint64_t bar_y_free[AZB_SY];         // P: stage of C's ring consumed (arrived by C)
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(16) float s_bias[AZT_C];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool prof_on = AZB_PROF && p.prof != nullptr && (blockIdx.x >> 1) == 0 && lane == 0;
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+    const long long prof_t0 = clock64();
     if (tid == 0) {
         azt_mbar_init(&bar_w, 1);
-        for (int i = 0; i < AZB_SMAX; i++) azt_mbar_init(&bar_in_full[i], 1);
-        for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
-        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
+        for (int i = 0; i < AZB_SMAX; i++) azt_mbar_init(&bar_in_full[i], 1);   // one bulk transfer per stage
         for (int i = 0; i < AZB_TMAX; i++) {
-            azt_mbar_init(&bar_out_empty[i], 1);        // P: relay a of C; C: the storer
+            azt_mbar_init(&bar_out_empty[i], 1);        // P: C's relay (the copy has landed); C: its storer
             azt_mbar_init(&bar_out_done[i], 8);         // one arrival per warp of the group that wrote the slab
         }
         for (int i = 0; i < AZB_SR; i++) {
             azt_mbar_init(&bar_res_full[i], 1);
             azt_mbar_init(&bar_res_empty[i], 8);        // the eight warps of the group that read it
         }
+        for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
+        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
         for (int i = 0; i < AZB_SY; i++) azt_mbar_init(&bar_y_free[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;");
         // C arms every stage of its input ring for the first slab P will copy into it
@@ -215,62 +262,52 @@ k_resblock(const azb_params p)
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
-    // both CTAs' barriers are initialised (and C's ring armed) before either touches the other's
+    // both CTAs' barriers are initialised (and C's ring zeroed) before either touches the other's
     azb_cluster_sync();
 
-    if (warp == 21) {
-        // ------------------------------------------------------- relay b (C) --
-        if (!isP && lane == 0) {
-            for (int j = 0; j < nslabs; j++) {
-                const int st = j % AZB_SY;
-                azt_mbar_wait(&bar_mma_done[j & 7], (j >> 3) & 1);
-                // MMA2(j) has read stage st: arm it for its next slab, then let P copy that slab in
-                if (j + AZB_SY < nslabs) {
-                    azt_mbar_expect_tx(&bar_in_full[st], AZT_OUT_BYTES);
-                    azb_remote_arrive(azb_remote(&bar_y_free[st], 0));
-                }
-            }
-        }
-    } else if (warp == 20) {
+    if (warp == 20) {
         // ------------------------------------------------------------ storer --
-        if (lane == 0 && isP) {
-            // finished y slab: staging tile -> rows 8..135 of stage st of C's input ring
+        if (isP && lane == 0 && !AZB_P_ASYNC) {
+            // P: finished y slab: staging tile -> rows 8..135 of stage st of C's input ring
             for (int j = 0; j < nslabs; j++) {
                 const int sb = j % AZB_TP, st = j % AZB_SY;
-                azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1);
-                if (j >= AZB_SY) azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1);
-                if (p.dbg_y) {
-                    azt_bulk_s2g(p.dbg_y + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
-                                 AZT_OUT_BYTES);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1));
+                if (j >= AZB_SY) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1));
                 azb_bulk_s2s(azb_remote(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, 1),
                              s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES, azb_remote(&bar_in_full[st], 1));
             }
-            if (p.dbg_y) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        } else if (lane == 0) {
+        } else if (!isP && lane == 0) {
+            // C: finished output slab -> global memory, in place
             for (int j = 0; j < nslabs; j++) {
                 const int sb = j % AZB_TC;
-                azt_mbar_wait(&bar_out_done[sb], (j / AZB_TC) & 1);
-                azt_bulk_s2g(p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
-                             AZT_OUT_BYTES);
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TC) & 1));
+                if (!(p.debug & 2))
+                    azt_bulk_s2g(p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
+                                 AZT_OUT_BYTES);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // hand the tile back as soon as the store has READ it (the write to global
-                // memory goes on): with two tiles the two epilogue groups must not wait for
-                // each other's stores to be issued
+                // memory goes on): each epilogue group has one tile
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 azt_mbar_arrive(&bar_out_empty[sb]);
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp == 19) {
-        // ------------------------------------------------------- relay a (C) --
+        // --------------------------------------------------------- relay (C) --
         if (!isP && lane == 0) {
-            for (int j = 0; j < nslabs; j++) {
-                // slab j has landed in C: P's staging tile that held it may be rewritten
-                azb_wait_cluster(&bar_in_full[j % AZB_SY], (j / AZB_SY) & 1);
-                azb_remote_arrive(azb_remote(&bar_out_empty[j % AZB_TP], 0));
+            for (int j = 0; j <= nslabs; j++) {
+                if (j < nslabs && !AZB_P_ASYNC) {
+                    // slab j has landed in C: P's staging tile that held it may be rewritten
+                    AZB_TIMED(0, azb_wait_cluster(&bar_in_full[j % AZB_SY], (j / AZB_SY) & 1));
+                    azb_remote_arrive(azb_remote(&bar_out_empty[j % AZB_TP], 0));
+                }
+                if (j >= 1 && j - 1 + AZB_SY < nslabs) {
+                    // MMA2(j-1) has read its stage: arm it for its next slab, then let P copy that in
+                    const int k = j - 1;
+                    AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[k & 7], (k >> 3) & 1));
+                    azt_mbar_expect_tx(&bar_in_full[k % AZB_SY], AZT_OUT_BYTES);
+                    azb_remote_arrive(azb_remote(&bar_y_free[k % AZB_SY], 0));
+                }
             }
         }
     } else if (warp == 18) {
@@ -283,17 +320,17 @@ k_resblock(const azb_params p)
                 for (int j = 0; j < nslabs; j++) {
                     const int st = j % AZB_SX;
                     // the stage is free once the MMAs of the slab that used it last have retired
-                    if (j >= AZB_SX) azt_mbar_wait(&bar_mma_done[(j - AZB_SX) & 7], ((j - AZB_SX) >> 3) & 1);
+                    if (j >= AZB_SX) AZB_TIMED(0, azt_mbar_wait(&bar_mma_done[(j - AZB_SX) & 7], ((j - AZB_SX) >> 3) & 1));
                     // slab rows plus 8 rows on each side: global rows [128 q, 128 q + 144)
                     azt_mbar_expect_tx(&bar_in_full[st], AZT_CHUNK_BYTES);
                     azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES, p.x + (size_t)((q0 + j) * 128) * AZT_ROW,
                                  AZT_CHUNK_BYTES, &bar_in_full[st]);
                 }
-            } else {
+            } else if (!(p.debug & 4)) {
                 // the residual: the block's own input slab, again (L2: P has just read it)
                 for (int j = 0; j < nslabs; j++) {
                     const int sr = j % AZB_SR;
-                    azt_mbar_wait(&bar_res_empty[sr], ((j / AZB_SR) & 1) ^ 1);
+                    AZB_TIMED(0, azt_mbar_wait(&bar_res_empty[sr], ((j / AZB_SR) & 1) ^ 1));
                     azt_mbar_expect_tx(&bar_res_full[sr], AZT_OUT_BYTES);
                     azt_bulk_g2s(s_res + sr * AZT_OUT_BYTES, p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW,
                                  AZT_OUT_BYTES, &bar_res_full[sr]);
@@ -315,10 +352,12 @@ k_resblock(const azb_params p)
             const int top = j + 1 - dy0;
             // highest output slab entered by the slabs before this one
             const int entered = j == 0 ? -1 : (y == 0 ? j - 1 : j);
-            azb_wait_cluster(&bar_in_full[st], (j / S) & 1);
+            AZB_TIMED(0, azb_wait_cluster(&bar_in_full[st], (j / S) & 1));
+            // st.async variant: the slab was not written by the async proxy the tensor core reads through
+            if (AZB_P_ASYNC && !isP) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             // a block entered for a new output slab t: its previous tenant t-8 must have been retired
             for (int t = entered + 1; t <= top; t++)
-                if (t >= 8) azt_mbar_wait(&bar_blk_free[AZB_RING(t)], ((t >> 3) - 1) & 1);
+                if (t >= 8) AZB_TIMED(2, azt_mbar_wait(&bar_blk_free[AZB_RING(t)], ((t >> 3) - 1) & 1));
             const int blk = AZB_RING(top), nb = dy1 - dy0 + 1;
             const int first = nb < 8 - blk ? nb : 8 - blk, second = nb - first;     // split where the ring wraps
             const uint32_t d0 = tmem + blk * 64, i0 = AZT_IDESC(first), i1 = AZT_IDESC(second);
@@ -327,11 +366,15 @@ k_resblock(const azb_params p)
             const uint64_t db0 = db_base + (uint64_t)(dy0 * 64 * (AZT_ROW / 16));
             const uint64_t db1 = db0 + (uint64_t)(first * 64 * (AZT_ROW / 16));
             // take the turn: the other warp has issued slab j-1
+            const long long tt_ = prof_on ? clock64() : 0;
             if (w == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
             else asm volatile("bar.sync 4, 64;" ::: "memory");
             asm volatile("tcgen05.fence::after_thread_sync;");
+            const long long ti_ = prof_on ? clock64() : 0;
+            if (prof_on) prof_acc[3] += ti_ - tt_;
             if (azt_elect()) {
-                if (second == 0) {
+                if (p.debug & 8) {
+                } else if (second == 0) {
 #pragma unroll
                     for (int dx = 0; dx < 3; dx++)
 #pragma unroll
@@ -360,6 +403,7 @@ k_resblock(const azb_params p)
                 if (w == 0) asm volatile("bar.arrive 4, 64;" ::: "memory");
                 else asm volatile("bar.arrive 3, 64;" ::: "memory");
             }
+            if (prof_on) prof_acc[4] += clock64() - ti_;
         }
     } else {
         // ----------------------------------------------------- epilogue --
@@ -375,52 +419,43 @@ k_resblock(const azb_params p)
             const int sb = j % T;
             uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
             uint4 rv[4];
-            if (!isP) {
+            if (!isP && !(p.debug & 4)) {
                 // this thread's row and channels of the residual slab, from the bulk-loaded ring
                 const int sr = j % AZB_SR;
-                azt_mbar_wait(&bar_res_full[sr], (j / AZB_SR) & 1);
+                AZB_TIMED(2, azt_mbar_wait(&bar_res_full[sr], (j / AZB_SR) & 1));
                 const uint4 *rrow = reinterpret_cast<const uint4 *>(s_res + sr * AZT_OUT_BYTES + l * AZT_ROW);
 #pragma unroll
                 for (int c = 0; c < 4; c++) rv[c] = rrow[(half * 4 + c) ^ sw];
                 // The release below hands the stage to the NEXT BULK LOAD (async proxy).  An
                 // mbarrier arrive does not wait for the shared-memory loads issued before it:
                 // without this the arrive overtook them and slow warps read the slab that was
-                // loaded three slabs later (tools/probe/block_diag2.py found exactly that, in
-                // ~2 % of the rows).  Consuming the loaded registers in a warp vote makes every
-                // lane's loads return before lane 0 can arrive.  (fence.proxy.async here is the
-                // other cure and costs 4 %; __threadfence_block is not one.)
+                // loaded three slabs later (~2 % of the rows; profiles/r02_fused_block.txt).
+                // Consuming the loaded registers in a warp vote makes every lane's loads return
+                // before lane 0 can arrive.  (fence.proxy.async here is the other cure and costs
+                // 4 %; __threadfence_block is not one.)
                 if (__any_sync(0xffffffffu, (rv[0].x ^ rv[1].y ^ rv[2].z ^ rv[3].w) == 0x7fc1a55eu &&
                                                 (rv[0].y ^ rv[1].x) == 0x5ea1c0deu && rv[2].x == 0xfeedbeefu))
                     asm volatile("nanosleep.u32 1;");
                 __syncwarp();
                 if (lane == 0) azt_mbar_arrive(&bar_res_empty[sr]);
-                if (p.dbg_cnt) {
-                    // probe: the same chunks straight from global memory win, mismatches are counted
-                    const uint4 *grow = reinterpret_cast<const uint4 *>(
-                        p.x + (size_t)(AZT_HALO + (q0 + j) * 128 + l) * AZT_ROW);
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        const uint4 gv = grow[(half * 4 + c) ^ sw];
-                        if (gv.x != rv[c].x || gv.y != rv[c].y || gv.z != rv[c].z || gv.w != rv[c].w) {
-                            const unsigned k = atomicAdd(p.dbg_cnt, 1u);
-                            if (k < 256) {      // record: where, and what the ring held
-                                unsigned *rec = p.dbg_cnt + 16 + 8 * k;
-                                rec[0] = (unsigned)(q0 + j); rec[1] = (unsigned)l; rec[2] = (unsigned)(half * 4 + c);
-                                rec[3] = (unsigned)j;
-                                rec[4] = rv[c].x; rec[5] = rv[c].y; rec[6] = rv[c].z; rec[7] = rv[c].w;
-                            }
-                        }
-                        rv[c] = gv;
-                    }
-                }
             }
-            // the staging tile must have been drained by the copy / store that used it last
-            if (isP) azb_wait_cluster(&bar_out_empty[sb], ((j / T) & 1) ^ 1);
-            else azt_mbar_wait(&bar_out_empty[sb], ((j / T) & 1) ^ 1);
+            uint32_t ybase = 0, ybar = 0;
+            if (AZB_P_ASYNC && isP) {
+                // row 8 + l of stage st of C's ring, once MMA2 has retired the slab that was there
+                const int st = j % AZB_SY;
+                if (lane == 0) AZB_TIMED(0, azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1));
+                __syncwarp();
+                ybase = azb_remote(s_in + st * AZT_CHUNK_BYTES + (8 + l) * AZT_ROW, 1);
+                ybar = azb_remote(&bar_in_full[st], 1);
+            } else {
+                // the staging tile must have been drained by the copy / store that used it last
+                AZB_TIMED(0, azb_wait_cluster(&bar_out_empty[sb], ((j / T) & 1) ^ 1));
+            }
             // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
             const int last = y + 1 < n ? j + 1 : j;
-            azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1);
+            AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
+            const long long tb_ = prof_on ? clock64() : 0;
             const int blk = AZB_RING(j);
             const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u + (uint32_t)half * 32u;
 #pragma unroll
@@ -429,6 +464,7 @@ k_resblock(const azb_params p)
                 AZT_TMEM_LD16(acc, ta + h * 16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;");
                 azt_tmem_zero16(ta + h * 16);       // retire: zero for the block's next output slab
+                uint4 o[2];  // (two chunks of this pass)
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     const int c8 = half * 4 + h * 2 + g;            // 8-channel chunk of the row
@@ -439,7 +475,7 @@ k_resblock(const azb_params p)
                     f[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
                     f[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
                     f[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
-                    if (!isP) {
+                    if (!isP && !(p.debug & 4)) {
                         const uint4 r = rv[h * 2 + g];
                         const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -454,7 +490,10 @@ k_resblock(const azb_params p)
                         __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
                         ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
                     }
-                    srow[c8 ^ sw] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    o[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    // chunk c8 of the row, at its swizzled place in the staging tile / in C's stage
+                    if (AZB_P_ASYNC && isP) azb_st_async(ybase + (uint32_t)((c8 ^ sw) << 4), o[g], ybar);
+                    else srow[c8 ^ sw] = o[g];
                 }
             }
             // hand the ring block back
@@ -462,13 +501,24 @@ k_resblock(const azb_params p)
             asm volatile("tcgen05.fence::before_thread_sync;");
             __syncwarp();
             if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
-            // staging tile complete: the storer sends it on (async proxy reads it)
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);
+            if (!(AZB_P_ASYNC && isP)) {
+                // staging tile complete: the storer sends it on (the copy engine, async proxy, reads it)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);
+            }
+            if (prof_on) prof_acc[3] += clock64() - tb_;
         }
     }
 #undef AZB_RING
+    if (prof_on && (warp == 0 || warp == 8 || warp >= 16)) {
+        // rows: rank x {epilogue g0, epilogue g1, mma even, mma odd, loader, relay, storer}
+        const int role = warp == 0 ? 0 : warp == 8 ? 1 : warp - 14;
+        unsigned long long *row = p.prof + ((size_t)rank * 7 + role) * 8;
+        for (int k = 0; k < 6; k++) row[k] = (unsigned long long)prof_acc[k];
+        row[6] = (unsigned long long)(clock64() - prof_t0);
+        row[7] = (unsigned long long)nslabs;
+    }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     // neither CTA may leave while the other can still reach into its shared memory

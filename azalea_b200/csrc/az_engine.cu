@@ -1176,12 +1176,11 @@ int az_nn_resblock_clusters(void)
     return azb_max_clusters[az_current_device()];
 }
 
-static void *azb_dbg_y = nullptr;
-static unsigned *azb_dbg_cnt = nullptr;
-
-/* probe hook (tools/probe/block_diag.py; not part of the ABI): the next launches also write the
- * intermediate slabs to y_dev and count residual-ring mismatches in cnt_dev (NULL, NULL = off) */
-void azb_set_debug(void *y_dev, unsigned *cnt_dev) { azb_dbg_y = y_dev; azb_dbg_cnt = cnt_dev; }
+static int azb_debug = 0;
+static unsigned long long *azb_prof = nullptr;
+/* probe hooks, not part of the ABI (tools/probe/block_time.py) */
+void azb_set_debug(int flags) { azb_debug = flags; }
+void azb_set_prof(unsigned long long *prof_dev) { azb_prof = prof_dev; }
 
 int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, int board_size,
                    int64_t num_boards, void *stream)
@@ -1193,7 +1192,8 @@ int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, int bo
     p.x = (uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
-    p.dbg_y = (uint8_t *)azb_dbg_y; p.dbg_cnt = azb_dbg_cnt;
+    p.debug = azb_debug;
+    p.prof = azb_prof;
     // clusters of two CTAs (one per SM) that can be resident at once on this device
     int *max_clusters = azb_max_clusters;
     const int dev = az_current_device();
@@ -1220,7 +1220,7 @@ int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, int bo
     return az_check(cudaGetLastError());
 }
 
-static_assert(AZB_SMEM_BYTES + 1024 <= 232448, "k_resblock: dynamic + static shared memory per CTA");
+static_assert(AZB_SMEM_BYTES + 2048 <= 232448, "k_resblock: dynamic + static shared memory per CTA");
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)
 {

@@ -73,16 +73,16 @@
                             // of the SM-to-SM link keep P's epilogue busy 2600 cycles per slab
                             // (0.65 ms per block against 0.59)
 #ifndef AZB_SX
-#define AZB_SX (AZB_P_ASYNC ? 8 : 5)    // P: input ring stages (x chunks, bulk loads)
+#define AZB_SX (AZB_P_ASYNC ? 8 : 4)    // P: input ring stages (x chunks, bulk loads)
 #endif
 #ifndef AZB_TP
-#define AZB_TP 3            // P: staging tiles (bulk-copy variant only)
+#define AZB_TP 4            // P: staging tiles (bulk-copy variant only)
 #endif
 #ifndef AZB_SY
 #define AZB_SY 4            // C: input ring stages (y slabs copied in by P)
 #endif
 #ifndef AZB_SR
-#define AZB_SR 3            // C: residual ring stages (x slabs, bulk loads)
+#define AZB_SR 2            // C: residual ring stages (x slabs, bulk loads)
 #endif
 #ifndef AZB_TC
 #define AZB_TC 2            // C: staging tiles
@@ -96,7 +96,14 @@
 #define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_SR + AZB_TC) * AZT_OUT_BYTES)
 #define AZB_SMEM_BYTES (AZB_SMEM_P > AZB_SMEM_C ? AZB_SMEM_P : AZB_SMEM_C)
 static_assert(AZB_SX <= 8 && AZB_SY <= 8, "stage reuse is tracked through the 8 MMA-retired barriers");
-static_assert(AZB_TC % 2 == 0, "each epilogue group of C owns its staging tiles");
+// Every ring that the two epilogue groups of a CTA share has an EVEN number of entries, so an
+// entry always belongs to the same group (slab parity).  A parity wait then cannot be two
+// phases away from its barrier: with three residual stages shared by both groups, a bulk load
+// that completed late let the other group pass the wait of the NEXT use of the stage -- wrong
+// residuals, and with the arrival counts mixed up, a hang or a launch failure when two
+// instances ran concurrently on two streams (tools/soak.py --streams 2).
+static_assert(AZB_TC % 2 == 0 && AZB_SR % 2 == 0 && (AZB_P_ASYNC || AZB_TP % 2 == 0),
+              "rings shared by the two epilogue groups must have an even number of entries");
 static_assert(!AZB_P_ASYNC || AZB_SY % 2 == 0, "st.async variant: a stage of C's ring belongs to one epilogue group of P");
 
 struct azb_params {

@@ -158,11 +158,18 @@ __global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32, MAXS <= 4 ? 8 : 3)
 k_select(az_engine e, az_select_args a)
 {
     __shared__ uint32_t smask_all[AZ_WARPS_PER_CTA][64];
+    // The game's hottest tree level, the root's children, staged in shared memory for the
+    // batch: every one of the `batch` descents starts by scoring all of them
+    // (search_tree.py:192-204 slices the same arrays once per descent), and the virtual
+    // losses of the batch (mcts.py:69-72) land on them first.  Read from the pool once,
+    // updated in place here, the touched records written back once.
+    __shared__ uint4 sroot_all[AZ_WARPS_PER_CTA][MAXS * 32];
     const int lane = az_lane();
     const int wib = threadIdx.x >> 5;
     const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + wib;
     if (g >= e.g1) return;
     uint32_t *smask = smask_all[wib];
+    uint4 *sroot = sroot_all[wib];
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     int4 *info = e.leaf_info + (size_t)g * e.B;
     const int status = meta[M_STATUS];
@@ -210,6 +217,14 @@ k_select(az_engine e, az_select_args a)
     const int ply = meta[M_PLY];
     int my_leaf = -1, my_depth = 0;         // lane b remembers descent b
     unsigned long long sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0, term = 0;
+    const int k0 = (int)(rootlink & AZ_LINK_KMASK), fc0 = (int)(rootlink >> AZ_LINK_KBITS);
+    uint32_t touched = 0;                   // bit s: this lane's root child lane + 32 s took a virtual loss
+#pragma unroll
+    for (int s = 0; s < MAXS; s++) {
+        const int j = lane + 32 * s;
+        if (j < k0) sroot[j] = nodes[fc0 + j];
+    }
+    __syncwarp();
 
     for (int b = 0; b < a.batch; b++) {
         uint32_t x = rx, o = ro, link = rootlink;
@@ -223,7 +238,7 @@ k_select(az_engine e, az_select_args a)
 #pragma unroll
             for (int s = 0; s < MAXS; s++) {
                 int j = lane + 32 * s;
-                rec[s] = j < k ? nodes[fc + j] : make_uint4(0, 0, 0, 0);
+                rec[s] = j < k ? (depth == 0 ? sroot[j] : nodes[fc + j]) : make_uint4(0, 0, 0, 0);
                 ni += (int)__uint_as_float(rec[s].x);
             }
             // score_actions, mcts.py:119-136.  sum(N) is a sum of small
@@ -293,8 +308,14 @@ k_select(az_engine e, az_select_args a)
             if (lane == owner) {
                 float2 nw = make_float2(__fadd_rn(__uint_as_float(cn), 1.0f),
                                         __fadd_rn(__uint_as_float(cw), 1.0f));
-                *reinterpret_cast<float2 *>(&nodes[node]) = nw;
+                if (depth == 0) {
+                    *reinterpret_cast<float2 *>(&sroot[jstar]) = nw;
+                    touched |= 1u << slot;
+                } else {
+                    *reinterpret_cast<float2 *>(&nodes[node]) = nw;
+                }
             }
+            if (depth == 0) __syncwarp();       // the next descent's lanes read the staged level
             // ForwardSearchIterator.step, search_tree.py:298-308
             tile = az_kth_empty(~(x | o) & valid, jstar, e.NW);
             if (lane == (tile >> 5)) {
@@ -342,7 +363,10 @@ k_select(az_engine e, az_select_args a)
         const int depth = __shfl_sync(AZ_FULL, my_depth, b);
         const uint32_t *path = pathg + (size_t)b * e.path_stride;
         for (int dd = lane; dd < depth; dd += 32) {
-            float2 *p = reinterpret_cast<float2 *>(&nodes[path[dd] & AZ_MAX_NODE]);
+            const int nd = (int)(path[dd] & AZ_MAX_NODE);
+            // level 0 of every path is a root child: staged
+            float2 *p = dd == 0 ? reinterpret_cast<float2 *>(&sroot[nd - fc0])
+                                : reinterpret_cast<float2 *>(&nodes[nd]);
             float2 nw = *p;
             nw.x = __fadd_rn(nw.x, -1.0f);
             nw.y = __fadd_rn(nw.y, -1.0f);
@@ -350,6 +374,13 @@ k_select(az_engine e, az_select_args a)
         }
         __syncwarp();
     }
+    // the touched root children go back to the pool: N and W after apply + undo, i.e. with the
+    // fp32 rounding of (W + 1) - 1 the reference leaves behind (mcts.py:79-92)
+#pragma unroll
+    for (int s = 0; s < MAXS; s++)
+        if ((touched >> s) & 1u)
+            *reinterpret_cast<float2 *>(&nodes[fc0 + lane + 32 * s]) =
+                *reinterpret_cast<const float2 *>(&sroot[lane + 32 * s]);
     if (lane == 0) {
         meta[M_SIM] = sim0 + a.batch;
         unsigned long long *cnt = e.counters + (size_t)g * AZ_CNT_PER_GAME;

@@ -68,7 +68,7 @@ class LockstepSelfPlay:
                  move_sampling=True, move_exploration=True, seed=0,
                  device=None, rank=0, world_size=1, nodes_per_game=None,
                  replay_rows=None, collect_replay=True, cuda_graph=True,
-                 max_plies=300, random_play=False, streams=1):
+                 max_plies=300, random_play=False, streams=None):
         # random_play: RandomPolicy self-play (random_policy.py:25-41) -- no
         # search, uniform move choice and uniform moves_prob at every ply;
         # how the reference fills the replay buffer before training
@@ -118,10 +118,13 @@ class LockstepSelfPlay:
                 evaluator.to(self.device)
                 evaluator.prepare_inference()
             torch.backends.cudnn.benchmark = True
-        # streams > 1 (opt-in): the games are split into that many windows driven on separate
-        # streams, so the tree kernels of one window run under the evaluator of another
-        # (az_engine_set_window); results do not depend on it.  4 % faster with the network
-        # in the loop; little mileage yet, hence not the default.
+        # streams > 1: the games are split into that many windows driven on separate streams,
+        # so the tree kernels of one window run under the evaluator of another
+        # (az_engine_set_window); results do not depend on it (tested bit for bit).  With a
+        # network in the loop two windows are 6 % faster than one and the
+        # default; the stub evaluator has nothing to overlap with.
+        if streams is None:
+            streams = 1 if (self.is_stub or self.G < 64) else 2
         self.streams = max(1, min(int(streams), self.G))
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(self.streams - 1)]
         self.moves_done = 0

@@ -52,9 +52,9 @@ def parse_args():
     ap.add_argument('--skip-tree-only', action='store_true')
     ap.add_argument('--sims', type=int, default=800, help='simulations per move')
     ap.add_argument('--nodes-per-game', type=int, default=0)
-    ap.add_argument('--streams', type=int, default=1,
-                    help='windows of the games driven on separate streams (opt-in, see DESIGN.md 5)')
-    ap.add_argument('--preroll', type=int, default=60,
+    ap.add_argument('--streams', type=int, default=2,
+                    help='windows of the games driven on separate streams (network evaluator; DESIGN.md 5)')
+    ap.add_argument('--preroll', type=int, default=110,
                     help='stagger the games before the steady-state window: slot g is advanced by '
                          'g * PREROLL / G random plies (0 = time the opening only)')
     ap.add_argument('--skip-configs', action='store_true',

@@ -13,19 +13,26 @@ ap.add_argument('--evaluator', default='stub')
 ap.add_argument('--games', type=int, default=4096)
 ap.add_argument('--board', type=int, default=11)
 ap.add_argument('--moves', type=int, default=260)
+ap.add_argument('--streams', type=int, default=1)
+ap.add_argument('--seconds', type=float, default=0, help='run for this long instead of --moves')
 a = ap.parse_args()
 if a.evaluator == 'net':
     torch.manual_seed(0); ev = HexNetwork(a.board, 6, 64).eval().cuda()
 else:
     ev = StubEvaluator(2)
 sp = LockstepSelfPlay(ev, num_games=a.games, board_size=a.board, simulations=800,
-                      search_batch_size=10, exploration_coef=0.5, seed=3)
+                      search_batch_size=10, exploration_coef=0.5, seed=3, streams=a.streams)
 rows = []
 t0 = time.time()
-for m in range(a.moves):
+m = 0
+while (time.time() - t0 < a.seconds) if a.seconds else (m < a.moves):
     sp.step_move()
     if m % 8 == 7 and sp.eng.replay_count():
-        rows.append(sp.harvest())
+        r = sp.harvest()
+        if sum(len(x) for x in rows) < 1_500_000:   # keep a bounded sample for the oracle check
+            rows.append(r)
+    m += 1
+a.moves = m
 torch.cuda.synchronize()
 dt = time.time() - t0
 if sp.eng.replay_count():

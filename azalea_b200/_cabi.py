@@ -9,7 +9,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libazalea_b200.so')
+# AZALEA_B200_LIB: a probe build of the same sources (tools/probe), for A/B measurements only
+LIB_PATH = os.environ.get('AZALEA_B200_LIB') or os.path.join(_HERE, 'lib', 'libazalea_b200.so')
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), 'include', 'azalea_b200.h')
 
 AZ_OK = 0

@@ -162,16 +162,14 @@ __device__ __forceinline__ void azb_st_async(uint32_t dst_cluster, const uint4 &
                  ::"r"(dst_cluster), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(bar_cluster) : "memory");
 }
 
-// wait on an own barrier whose phase is completed from the other CTA
+// Wait on an own barrier whose phase is completed from the other CTA (a relaxed remote arrive,
+// or the bytes of its bulk copy).  The plain CTA-scope wait is enough: these barriers carry
+// flow control only -- what they guard was read or written by the tensor core or the copy
+// engine, never by the other CTA's threads -- and the cluster-scope acquire costs an L1
+// invalidation (CCTL.IVALL) per wait.
 __device__ __forceinline__ void azb_wait_cluster(uint64_t *bar, uint32_t parity)
 {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(done) : "r"(azt_smem(bar)), "r"(parity) : "memory");
-    }
+    azt_mbar_wait(bar, parity);
 }
 
 // one 32-byte sector of a row: 16-byte chunks lo | hi

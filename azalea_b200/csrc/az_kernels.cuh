@@ -20,6 +20,17 @@
 
 #include "az_common.cuh"
 
+// Shared-memory staging of the root's children for the descents of a batch (the north star's
+// "hot tree levels").  Built, bit-exact, measured (profiles/r02_k_select_staged.txt): under ncu
+// 44 % less DRAM traffic (97 vs 175 MB per launch) and 17 % fewer warp instructions (1901 vs 2290
+// per descent), but in the running step the launch is 6.7 % SLOWER (0.164 vs 0.154 ms, tree-only
+// 1.54e8 vs 1.61e8 simulations/s, A/B on the same box): the root level is re-read from L1 anyway
+// (58 % L1 hit rate), and staging adds a serial prologue, a warp barrier per descent and a
+// write-back to a kernel that is bound by latency and issue, not by bytes.  Off by default.
+#ifndef AZ_STAGE_ROOT
+#define AZ_STAGE_ROOT 0
+#endif
+
 struct az_select_args {
     int batch;
     float coef;
@@ -163,7 +174,7 @@ k_select(az_engine e, az_select_args a)
     // (search_tree.py:192-204 slices the same arrays once per descent), and the virtual
     // losses of the batch (mcts.py:69-72) land on them first.  Read from the pool once,
     // updated in place here, the touched records written back once.
-    __shared__ uint4 sroot_all[AZ_WARPS_PER_CTA][MAXS * 32];
+    __shared__ uint4 sroot_all[AZ_WARPS_PER_CTA][AZ_STAGE_ROOT ? MAXS * 32 : 1];
     const int lane = az_lane();
     const int wib = threadIdx.x >> 5;
     const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + wib;
@@ -219,12 +230,14 @@ k_select(az_engine e, az_select_args a)
     unsigned long long sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0, term = 0;
     const int k0 = (int)(rootlink & AZ_LINK_KMASK), fc0 = (int)(rootlink >> AZ_LINK_KBITS);
     uint32_t touched = 0;                   // bit s: this lane's root child lane + 32 s took a virtual loss
+    if (AZ_STAGE_ROOT) {
 #pragma unroll
-    for (int s = 0; s < MAXS; s++) {
-        const int j = lane + 32 * s;
-        if (j < k0) sroot[j] = nodes[fc0 + j];
+        for (int s = 0; s < MAXS; s++) {
+            const int j = lane + 32 * s;
+            if (j < k0) sroot[j] = nodes[fc0 + j];
+        }
+        __syncwarp();
     }
-    __syncwarp();
 
     for (int b = 0; b < a.batch; b++) {
         uint32_t x = rx, o = ro, link = rootlink;
@@ -238,7 +251,7 @@ k_select(az_engine e, az_select_args a)
 #pragma unroll
             for (int s = 0; s < MAXS; s++) {
                 int j = lane + 32 * s;
-                rec[s] = j < k ? (depth == 0 ? sroot[j] : nodes[fc + j]) : make_uint4(0, 0, 0, 0);
+                rec[s] = j < k ? (AZ_STAGE_ROOT && depth == 0 ? sroot[j] : nodes[fc + j]) : make_uint4(0, 0, 0, 0);
                 ni += (int)__uint_as_float(rec[s].x);
             }
             // score_actions, mcts.py:119-136.  sum(N) is a sum of small
@@ -308,14 +321,14 @@ k_select(az_engine e, az_select_args a)
             if (lane == owner) {
                 float2 nw = make_float2(__fadd_rn(__uint_as_float(cn), 1.0f),
                                         __fadd_rn(__uint_as_float(cw), 1.0f));
-                if (depth == 0) {
+                if (AZ_STAGE_ROOT && depth == 0) {
                     *reinterpret_cast<float2 *>(&sroot[jstar]) = nw;
                     touched |= 1u << slot;
                 } else {
                     *reinterpret_cast<float2 *>(&nodes[node]) = nw;
                 }
             }
-            if (depth == 0) __syncwarp();       // the next descent's lanes read the staged level
+            if (AZ_STAGE_ROOT && depth == 0) __syncwarp();       // the next descent's lanes read the staged level
             // ForwardSearchIterator.step, search_tree.py:298-308
             tile = az_kth_empty(~(x | o) & valid, jstar, e.NW);
             if (lane == (tile >> 5)) {
@@ -365,7 +378,7 @@ k_select(az_engine e, az_select_args a)
         for (int dd = lane; dd < depth; dd += 32) {
             const int nd = (int)(path[dd] & AZ_MAX_NODE);
             // level 0 of every path is a root child: staged
-            float2 *p = dd == 0 ? reinterpret_cast<float2 *>(&sroot[nd - fc0])
+            float2 *p = AZ_STAGE_ROOT && dd == 0 ? reinterpret_cast<float2 *>(&sroot[nd - fc0])
                                 : reinterpret_cast<float2 *>(&nodes[nd]);
             float2 nw = *p;
             nw.x = __fadd_rn(nw.x, -1.0f);
@@ -376,11 +389,13 @@ k_select(az_engine e, az_select_args a)
     }
     // the touched root children go back to the pool: N and W after apply + undo, i.e. with the
     // fp32 rounding of (W + 1) - 1 the reference leaves behind (mcts.py:79-92)
+    if (AZ_STAGE_ROOT) {
 #pragma unroll
-    for (int s = 0; s < MAXS; s++)
-        if ((touched >> s) & 1u)
-            *reinterpret_cast<float2 *>(&nodes[fc0 + lane + 32 * s]) =
-                *reinterpret_cast<const float2 *>(&sroot[lane + 32 * s]);
+        for (int s = 0; s < MAXS; s++)
+            if ((touched >> s) & 1u)
+                *reinterpret_cast<float2 *>(&nodes[fc0 + lane + 32 * s]) =
+                    *reinterpret_cast<const float2 *>(&sroot[lane + 32 * s]);
+    }
     if (lane == 0) {
         meta[M_SIM] = sim0 + a.batch;
         unsigned long long *cnt = e.counters + (size_t)g * AZ_CNT_PER_GAME;

@@ -78,6 +78,99 @@ class _TrainingPlayer:
         self.player.stop()
 
 
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def _comm_device(net_device, group=None):
+    """NCCL moves device tensors, gloo host tensors."""
+    import torch.distributed as dist
+    return net_device if 'nccl' in str(dist.get_backend(group)) else torch.device('cpu')
+
+
+def broadcast_policy_weights(net, src: int = 0, group=None) -> int:
+    """The trainer's network to every self-play rank ("weight
+    broadcast rank 0 -> all when the trainer updates the net"; the reference
+    gets the same effect by pickling the agent into every game it dispatches,
+    parallel_player.py:36-38).  Parameters and buffers (BatchNorm statistics)
+    travel as one flat tensor per dtype; returns the bytes sent.  No-op
+    without a process group."""
+    dist = _dist()
+    if dist is None:
+        return 0
+    tensors = [p.data for p in net.parameters()] + list(net.buffers())
+    by_dtype: Dict = {}
+    for t in tensors:
+        by_dtype.setdefault(t.dtype, []).append(t)
+    nbytes = 0
+    for ts in by_dtype.values():
+        dev = _comm_device(ts[0].device, group)
+        flat = torch.cat([t.reshape(-1) for t in ts]).to(dev)
+        dist.broadcast(flat, src=src, group=group)
+        off = 0
+        for t in ts:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+        nbytes += flat.numel() * flat.element_size()
+    return nbytes
+
+
+class DistributedSelfPlay:
+    """Replay refills played by ALL ranks of the process group for the one
+    rank that trains.  Rank 0 calls ``read_device(size)`` wherever
+    the single-GPU loop calls its player; the other ranks sit in ``serve()``.
+    Per refill: one broadcast of the request, one broadcast of the weights
+    (~2 MB), every rank plays ``ceil(size / world)`` positions with its own
+    games, and the rows are gathered to rank 0 (``gather_replay_rows``, the
+    path's only data exchange).  ``stop()`` on rank 0 releases the servers."""
+
+    def __init__(self, player, net, group=None):
+        self.player, self.net, self.group = player, net, group
+        self.bytes_broadcast = 0
+
+    def _header(self, value=0):
+        import torch.distributed as dist
+        dev = _comm_device(next(self.net.parameters()).device, self.group)
+        h = torch.tensor([int(value)], dtype=torch.int64, device=dev)
+        dist.broadcast(h, src=0, group=self.group)
+        return int(h.item())
+
+    def _play_and_gather(self, size):
+        import torch.distributed as dist
+        from .selfplay import gather_replay_rows
+        world = dist.get_world_size(self.group)
+        self.bytes_broadcast += broadcast_policy_weights(self.net, 0, self.group)
+        rows, metrics = self.player.read_device(-(-size // world))
+        rows = rows.to(_comm_device(rows.device, self.group))
+        return gather_replay_rows(rows, dst=0, group=self.group), metrics
+
+    def read_device(self, size: int):
+        """Rank 0: ask every rank for its share and collect the rows."""
+        self._header(size)
+        rows, metrics = self._play_and_gather(int(size))
+        return rows, metrics
+
+    def serve(self) -> int:
+        """Ranks > 0: play refills until rank 0 stops.  Returns how many."""
+        served = 0
+        while True:
+            size = self._header()
+            if size < 0:
+                return served
+            self._play_and_gather(size)
+            served += 1
+
+    def stop(self):
+        import torch.distributed as dist
+        if dist.get_rank(self.group) == 0:
+            self._header(-1)
+        self.player.stop()
+
+
 def train(policy, config, rundir, *,
           replaybuf: Optional[DeviceReplayBuffer] = None,
           max_steps: Optional[int] = None) -> str:
@@ -103,6 +196,24 @@ def train(policy, config, rundir, *,
 
     game_class = _game_class(config['game'])
     game_factory = partial(game_class, board_size=config['board_size'])
+
+    # Under torch.distributed (one process per GPU): rank 0 trains, every rank plays
+    # self-play for its refills with its own block of game ids
+    dist = _dist()
+    rank = dist.get_rank() if dist else 0
+    world = dist.get_world_size() if dist else 1
+    if rank > 0:
+        policy.net.to(device)
+        policy.settings['move_exploration'] = True
+        policy.settings['move_sampling'] = True
+        agent = AzaleaAgent(game_factory, policy=policy, device=str(device))
+        worker = DistributedSelfPlay(
+            _TrainingPlayer(Player(None, [agent], num_games=num_games, seed=seed & 0x7fffffff,
+                                   device=device, rank=rank, world_size=world), policy.net),
+            policy.net)
+        served = worker.serve()
+        logging.info(f'rank {rank}: served {served} replay refills')
+        return ''
 
     # initialize replay buffer with random policy
     if replaybuf is None:
@@ -135,7 +246,9 @@ def train(policy, config, rundir, *,
     # instantiate game and wrap it together with policy
     agent = AzaleaAgent(game_factory, policy=policy, device=str(device))
     player = _TrainingPlayer(Player(None, [agent], num_games=num_games, seed=seed & 0x7fffffff,
-                                    device=device), policy.net)
+                                    device=device, rank=rank, world_size=world), policy.net)
+    if dist:
+        player = DistributedSelfPlay(player, policy.net)
     sampler = torch.Generator(device=device)
     sampler.manual_seed(seed)
 

@@ -257,3 +257,79 @@ def test_tournament_sharding_and_reduce_two_ranks_gloo():
     share1 = evaluate(agents, 7, rank=1, world_size=2, reduce=False, _play=_fake_play)
     assert got[1] == share1                     # rank 1 keeps its own share
     assert sum(sum(v) for v in share1.values()) == 35
+
+
+class _FakePlayer:
+    """read_device() of a self-play player, without a GPU: rows tagged with
+    the rank and with a digest of the weights the rank played with."""
+
+    def __init__(self, rank, net):
+        self.rank, self.net, self.calls = rank, net, 0
+
+    def read_device(self, size):
+        self.calls += 1
+        rows = torch.zeros(size, 48, dtype=torch.uint8)
+        rows[:, 0] = self.rank
+        rows[:, 1] = self.calls
+        rows[:, 2] = int(round(float(self.net.weight.sum()))) % 251
+        return rows, {'games': 1}
+
+    def stop(self):
+        pass
+
+
+def _refill_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from azalea_b200.policy_trainer import DistributedSelfPlay
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}',
+                            rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)                   # the ranks start with different weights
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.BatchNorm1d(3))
+    sp = DistributedSelfPlay(_FakePlayer(rank, net[0]), net)
+    if rank == 0:
+        out = []
+        for step in range(3):
+            with torch.no_grad():
+                net[0].weight.fill_(float(step + 1))        # "an optimizer step"
+                net[1].running_mean.fill_(0.5 * step)
+                net[1].num_batches_tracked.fill_(step)
+            rows, _ = sp.read_device(7)
+            out.append(rows.numpy().copy())
+        sp.stop()
+        q.put((rank, out, sp.bytes_broadcast))
+    else:
+        served = sp.serve()
+        q.put((rank, (served, net[0].weight.detach().numpy().copy(),
+                      net[1].running_mean.numpy().copy(), int(net[1].num_batches_tracked)), 0))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distributed_refill_protocol_two_ranks_gloo():
+    """SURVEY 8e, training hand-off: rank 0 trains and asks for replay rows;
+    before every refill its weights (parameters AND BatchNorm buffers) are
+    broadcast, every rank plays its share, rows are gathered to rank 0."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_refill_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (a, b) for r, a, b in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    refills, nbytes = got[0]
+    assert nbytes == 3 * (4 * (12 + 3 + 3 + 3 + 3 + 3) + 8)      # float tensors + the int64 counter, 3 times
+    for step, rows in enumerate(refills):
+        assert rows.shape == (8, 48)                    # ceil(7 / 2) rows from each rank
+        assert list(rows[:, 0]) == [0] * 4 + [1] * 4    # rank order
+        assert (rows[:, 1] == step + 1).all()
+        # both ranks played with the weights of this step: sum = 12 * (step + 1)
+        assert (rows[:, 2] == (12 * (step + 1)) % 251).all()
+    served, w, mean, tracked = got[1][0]
+    assert served == 3 and (w == 3.0).all() and (mean == 1.0).all() and tracked == 2

@@ -60,18 +60,28 @@
 //   warps 16,17  MMA issuers (even / odd slabs)
 //   warp 18      loader: weights; P: x chunks (144 rows); C: residual slabs (128 rows)
 //   warp 19      C: relay (slab landed -> P.out_empty; MMA2 retired -> re-arm, P.y_free)
-//   warp 20      storer: P: staging tile -> C's ring; C: staging tile -> global memory
+//   warp 20      storer: P: staging tile -> C's ring; C: staging tile -> x
 #pragma once
 
 #include "az_tower.cuh"
 
-#define AZB_THREADS 672
-#ifndef AZB_P_ASYNC
-#define AZB_P_ASYNC 0       // 0: y goes through a staging tile and a shared-to-shared bulk copy;
-#endif                      // 1 (probe): P's epilogue sends it with st.async, registers -> C's ring:
-                            // bit-exact too, but 4 x STAS.128 per thread and slab at the ~20 B/clock
-                            // of the SM-to-SM link keep P's epilogue busy 2600 cycles per slab
-                            // (0.65 ms per block against 0.59)
+#ifndef AZB_STORERS
+#define AZB_STORERS 1       // storer threads per CTA; 2 (probe): warps 20 / 21 take the even / odd slabs
+#endif
+#define AZB_THREADS (AZB_STORERS == 2 ? 704 : 672)
+// How y travels from P to C (all three are bit-exact; sustained-bench A/B on one box,
+// profiles/r02_fused_block.txt):
+//   0  staging tile + shared-to-shared bulk copy over the SM-to-SM link          9.22e6 sims/s
+//   2  (probe) through a small L2-resident scratch ring in global memory: P bulk-stores the
+//      staging tile, C bulk-loads it; the link carries only mbarrier arrives      8.96e6
+//   1  (probe) P's epilogue sends it with st.async, registers -> C's ring: 4 x STAS.128 per
+//      thread and slab keep P's epilogue busy 2600 cycles per slab                (0.65 ms burst)
+#ifndef AZB_HANDOVER
+#define AZB_HANDOVER 0
+#endif
+#define AZB_P_ASYNC (AZB_HANDOVER == 1)
+#define AZB_VIA_L2 (AZB_HANDOVER == 2)
+#define AZB_R 8             // scratch slots per cluster (16 KB each)
 #ifndef AZB_SX
 #define AZB_SX (AZB_P_ASYNC ? 8 : 4)    // P: input ring stages (x chunks, bulk loads)
 #endif
@@ -95,6 +105,7 @@
 #define AZB_SMEM_P (AZT_WBYTES + AZB_SX * AZT_CHUNK_BYTES + (AZB_P_ASYNC ? 0 : AZB_TP) * AZT_OUT_BYTES)
 #define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_SR + AZB_TC) * AZT_OUT_BYTES)
 #define AZB_SMEM_BYTES (AZB_SMEM_P > AZB_SMEM_C ? AZB_SMEM_P : AZB_SMEM_C)
+static_assert(AZB_SY <= AZB_R, "bar_y_free is sized for the scratch ring");
 static_assert(AZB_SX <= 8 && AZB_SY <= 8, "stage reuse is tracked through the 8 MMA-retired barriers");
 // Every ring that the two epilogue groups of a CTA share has an EVEN number of entries, so an
 // entry always belongs to the same group (slab parity).  A parity wait then cannot be two
@@ -113,6 +124,7 @@ struct azb_params {
     int n;                  // board size
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
+    uint8_t *scratch;       // AZB_VIA_L2: [clusters][AZB_R][16 KB] hand-over ring in global memory
     unsigned long long *prof;   // probe only: per-role wait cycles of cluster 0 ([rank][32]) or NULL
     int debug;              // probe only (tools/probe/block_time.py): 2 = C skips its global stores,
                             // 4 = C skips the residual loads, 8 = no MMAs
@@ -205,7 +217,8 @@ k_resblock(const azb_params p)
     __shared__ uint64_t bar_res_full[AZB_SR], bar_res_empty[AZB_SR];        // C: residual ring
     __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7
     __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
-    __shared__ uint64_t bar_y_free[AZB_SY];         // P: stage of C's ring consumed (arrived by C)
+    __shared__ uint64_t bar_y_free[AZB_R];          // P: stage of C's ring / scratch slot consumed (arrived by C)
+    __shared__ uint64_t bar_y_ready[AZB_R];         // C (AZB_VIA_L2): scratch slot written (arrived by P)
     __shared__ uint32_t tmem_holder;
     __shared__ __align__(16) float s_bias[AZT_C];
 
@@ -226,10 +239,10 @@ k_resblock(const azb_params p)
         }
         for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
         for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
-        for (int i = 0; i < AZB_SY; i++) azt_mbar_init(&bar_y_free[i], 1);
+        for (int i = 0; i < AZB_R; i++) { azt_mbar_init(&bar_y_free[i], 1); azt_mbar_init(&bar_y_ready[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;");
         // C arms every stage of its input ring for the first slab P will copy into it
-        if (!isP)
+        if (!isP && !AZB_VIA_L2)
             for (int i = 0; i < AZB_SY; i++) azt_mbar_expect_tx(&bar_in_full[i], AZT_OUT_BYTES);
     }
     if (tid < AZT_C) s_bias[tid] = p.bias[rank * AZT_C + tid];
@@ -270,9 +283,31 @@ k_resblock(const azb_params p)
     // both CTAs' barriers are initialised (and C's ring zeroed) before either touches the other's
     azb_cluster_sync();
 
-    if (warp == 20) {
-        // ------------------------------------------------------------ storer --
-        if (isP && lane == 0 && !AZB_P_ASYNC) {
+    if (warp >= 20) {
+        // ----------------------------------------------------------- storers --
+        // A bulk store takes ~1000 cycles to read its 16 KB tile, and bulk groups are per
+        // thread: one storer thread that waits for each store's read before it hands the tile
+        // back caps the pipeline AROUND the MMAs at ~1200 cycles per slab (measured with the MMAs
+        // switched off); two threads (AZB_STORERS 2: even / odd slabs) lift that to ~1000, but
+        // with the MMAs running the kernel is bound elsewhere and the extra warp costs 1 %.
+        const int sw_ = warp - 20;          // AZB_STORERS == 1: warp 20 takes every slab
+        if (isP && lane == 0 && AZB_VIA_L2) {
+            // P: finished y slab: staging tile -> slot j % AZB_R of the cluster's scratch ring
+            uint8_t *ring = p.scratch + (size_t)cid * AZB_R * AZT_OUT_BYTES;
+            for (int j = sw_; j < nslabs; j += AZB_STORERS) {
+                const int sb = j % AZB_TP, ss = j % AZB_R;
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1));
+                if (j >= AZB_R) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[ss], ((j / AZB_R) & 1) ^ 1));
+                azt_bulk_s2g(ring + (size_t)ss * AZT_OUT_BYTES, s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // the tile is free as soon as the store has READ it ...
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                azt_mbar_arrive(&bar_out_empty[sb]);
+                // ... and C may load the slab once the store has COMPLETED
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                azb_remote_arrive(azb_remote(&bar_y_ready[ss], 1));
+            }
+        } else if (isP && lane == 0 && !AZB_P_ASYNC && sw_ == 0) {
             // P: finished y slab: staging tile -> rows 8..135 of stage st of C's input ring
             for (int j = 0; j < nslabs; j++) {
                 const int sb = j % AZB_TP, st = j % AZB_SY;
@@ -283,7 +318,7 @@ k_resblock(const azb_params p)
             }
         } else if (!isP && lane == 0) {
             // C: finished output slab -> global memory, in place
-            for (int j = 0; j < nslabs; j++) {
+            for (int j = sw_; j < nslabs; j += AZB_STORERS) {
                 const int sb = j % AZB_TC;
                 AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TC) & 1));
                 if (!(p.debug & 2))
@@ -299,7 +334,26 @@ k_resblock(const azb_params p)
         }
     } else if (warp == 19) {
         // --------------------------------------------------------- relay (C) --
-        if (!isP && lane == 0) {
+        if (!isP && lane == 0 && AZB_VIA_L2) {
+            // C: y loader: scratch slot -> rows 8..135 of stage st of the input ring (an L2 hit), and,
+            // two slabs later, the slot back to P
+            const uint8_t *ring = p.scratch + (size_t)cid * AZB_R * AZT_OUT_BYTES;
+            for (int j = 0; j < nslabs + 2; j++) {
+                if (j < nslabs) {
+                    const int ss = j % AZB_R, st = j % AZB_SY;
+                    AZB_TIMED(0, azb_wait_cluster(&bar_y_ready[ss], (j / AZB_R) & 1));
+                    if (j >= AZB_SY) AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[(j - AZB_SY) & 7], ((j - AZB_SY) >> 3) & 1));
+                    azt_mbar_expect_tx(&bar_in_full[st], AZT_OUT_BYTES);
+                    azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, ring + (size_t)ss * AZT_OUT_BYTES,
+                                 AZT_OUT_BYTES, &bar_in_full[st]);
+                }
+                if (j >= 2 && j - 2 + AZB_R < nslabs) {
+                    const int k = j - 2;
+                    azt_mbar_wait(&bar_in_full[k % AZB_SY], (k / AZB_SY) & 1);
+                    azb_remote_arrive(azb_remote(&bar_y_free[k % AZB_R], 0));
+                }
+            }
+        } else if (!isP && lane == 0) {
             for (int j = 0; j <= nslabs; j++) {
                 if (j < nslabs && !AZB_P_ASYNC) {
                     // slab j has landed in C: P's staging tile that held it may be rewritten
@@ -517,9 +571,9 @@ k_resblock(const azb_params p)
     }
 #undef AZB_RING
     if (prof_on && (warp == 0 || warp == 8 || warp >= 16)) {
-        // rows: rank x {epilogue g0, epilogue g1, mma even, mma odd, loader, relay, storer}
+        // rows: rank x {epilogue g0, epilogue g1, mma even, mma odd, loader, relay, storer even, storer odd}
         const int role = warp == 0 ? 0 : warp == 8 ? 1 : warp - 14;
-        unsigned long long *row = p.prof + ((size_t)rank * 7 + role) * 8;
+        unsigned long long *row = p.prof + ((size_t)rank * 8 + role) * 8;
         for (int k = 0; k < 6; k++) row[k] = (unsigned long long)prof_acc[k];
         row[6] = (unsigned long long)(clock64() - prof_t0);
         row[7] = (unsigned long long)nslabs;

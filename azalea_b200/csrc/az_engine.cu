@@ -1182,16 +1182,23 @@ static unsigned long long *azb_prof = nullptr;
 void azb_set_debug(int flags) { azb_debug = flags; }
 void azb_set_prof(unsigned long long *prof_dev) { azb_prof = prof_dev; }
 
-int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, int board_size,
-                   int64_t num_boards, void *stream)
+size_t az_nn_resblock_scratch_bytes(void)
 {
-    if (!x_dev || !w_dev || !bias_dev || board_size < 2 || board_size > 19 || num_boards < 0)
+    /* only the AZB_HANDOVER == 2 probe build passes the intermediate slabs through global memory */
+    return AZB_VIA_L2 ? (size_t)(az_sm_count(az_current_device()) / 2) * AZB_R * AZT_OUT_BYTES : 0;
+}
+
+int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
+                   int board_size, int64_t num_boards, void *stream)
+{
+    if (!x_dev || !w_dev || !bias_dev || (AZB_VIA_L2 && !scratch_dev) || board_size < 2 || board_size > 19 || num_boards < 0)
         return AZ_E_INVALID;
     if (num_boards == 0) return AZ_OK;
     azb_params p = {};
     p.x = (uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
+    p.scratch = (uint8_t *)scratch_dev;
     p.debug = azb_debug;
     p.prof = azb_prof;
     // clusters of two CTAs (one per SM) that can be resident at once on this device

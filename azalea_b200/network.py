@@ -348,9 +348,11 @@ class HexNetwork(nn.Module):
             bufs = (torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
                     torch.zeros(rows, 64, dtype=torch.bfloat16, device=dev),
                     torch.zeros(N, wfc.shape[1], dtype=torch.bfloat16, device=dev),
-                    torch.empty(N, wfc.shape[0], dtype=torch.bfloat16, device=dev))
+                    torch.empty(N, wfc.shape[0], dtype=torch.bfloat16, device=dev),
+                    # hand-over ring of the fused residual block (csrc/az_block.cuh)
+                    torch.zeros(max(16, L.az_nn_resblock_scratch_bytes()), dtype=torch.uint8, device=dev))
             f['tower_buf'][(npad, dev, stream_id)] = bufs
-        x, y, flat, yfc = bufs
+        x, y, flat, yfc, scratch = bufs
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
@@ -372,7 +374,7 @@ class HexNetwork(nn.Module):
             # one launch per residual block (csrc/az_block.cuh), in place
             for w12, b12 in fused:
                 timed(lambda: _cabi.check(L.az_nn_resblock(
-                    p(x), p(w12), p(b12), n, npad, stream)), 'block')
+                    p(x), p(w12), p(b12), p(scratch), n, npad, stream)), 'block')
         else:
             for (w1, b1), (w2, b2) in f['tower']:
                 timed(lambda: _cabi.check(L.az_nn_conv3x3(

@@ -320,10 +320,17 @@ int az_nn_conv3x3(const void *x_dev, const void *w_dev, const float *bias_dev,
  * cluster of two CTAs, conv1 on one SM streaming its output slabs through
  * distributed shared memory into conv2 on the other).  x: slab layout as for
  * az_nn_conv3x3; w: the two layers' packed weights back to back
- * [2][3 kx][3 ky][64][64] bf16; bias f32 [2][64].  Bit-identical to
- * az_nn_conv3x3(x, w1, b1, NULL, y) followed by az_nn_conv3x3(y, w2, b2, x, x). */
+ * [2][3 kx][3 ky][64][64] bf16; bias f32 [2][64]; scratch: device memory of
+ * az_nn_resblock_scratch_bytes() bytes -- 0 in the shipped build, where the
+ * intermediate slabs travel through distributed shared memory, so NULL is
+ * fine; a probe build (AZB_HANDOVER=2) passes them through this ring instead
+ * (L2 resident; one per stream that launches concurrently).
+ * Bit-identical to az_nn_conv3x3(x, w1, b1, NULL, y) followed by
+ * az_nn_conv3x3(y, w2, b2, x, x). */
+size_t az_nn_resblock_scratch_bytes(void);
 int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev,
-                   int board_size, int64_t num_boards, void *stream);
+                   void *scratch_dev, int board_size, int64_t num_boards,
+                   void *stream);
 /* Diagnostic: how many two-CTA clusters az_nn_resblock sizes its grid for on
  * the current device (cudaOccupancyMaxActiveClusters; 74 on a B200), 0 before
  * the first launch. */

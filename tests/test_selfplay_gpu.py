@@ -466,10 +466,11 @@ def test_fused_resblock_equals_two_launches(n, N):
         _cabi.check(L.az_nn_conv3x3(p(ya), p(wp[2 * blk + 1]), p(bs[2 * blk + 1]), p(xa), p(xa), n, N, stream))
     # one launch per block
     xb = tl.to_slabs(x)
+    scratch = torch.zeros(max(16, L.az_nn_resblock_scratch_bytes()), dtype=torch.uint8, device='cuda')
     for blk in range(2):
         w12 = torch.cat([wp[2 * blk], wp[2 * blk + 1]]).contiguous()
         b12 = torch.cat([bs[2 * blk], bs[2 * blk + 1]]).contiguous()
-        _cabi.check(L.az_nn_resblock(p(xb), p(w12), p(b12), n, N, stream))
+        _cabi.check(L.az_nn_resblock(p(xb), p(w12), p(b12), p(scratch), n, N, stream))
     torch.cuda.synchronize()
     assert torch.equal(xa.view(torch.int16), xb.view(torch.int16))
     got, rest = tl.from_slabs(xb, n, N)
@@ -500,17 +501,19 @@ def test_fused_resblock_concurrent_streams():
     b12 = (torch.randn(128, device='cuda') * 0.1).contiguous()
     p = lambda t: ctypes.c_void_p(t.data_ptr())
     ref = tl.to_slabs(x)
+    # one hand-over ring per stream that launches concurrently
+    scr = [torch.zeros(max(16, L.az_nn_resblock_scratch_bytes()), dtype=torch.uint8, device='cuda') for _ in range(2)]
     st0 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     reps = 30
     for _ in range(reps):
-        _cabi.check(L.az_nn_resblock(p(ref), p(w12), p(b12), n, N, st0))
+        _cabi.check(L.az_nn_resblock(p(ref), p(w12), p(b12), p(scr[0]), n, N, st0))
     torch.cuda.synchronize()
     streams = [torch.cuda.Stream() for _ in range(2)]
     bufs = [tl.to_slabs(x) for _ in streams]
     torch.cuda.synchronize()
     for _ in range(reps):
-        for s, b in zip(streams, bufs):
-            _cabi.check(L.az_nn_resblock(p(b), p(w12), p(b12), n, N, ctypes.c_void_p(s.cuda_stream)))
+        for s, b, sc in zip(streams, bufs, scr):
+            _cabi.check(L.az_nn_resblock(p(b), p(w12), p(b12), p(sc), n, N, ctypes.c_void_p(s.cuda_stream)))
     torch.cuda.synchronize()
     for b in bufs:
         assert torch.equal(b.view(torch.int16), ref.view(torch.int16))

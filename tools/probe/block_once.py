@@ -10,6 +10,8 @@ x[8:rows - 16] = (torch.rand(rows - 24, 64, device='cuda') * 0.1).to(torch.bfloa
 w = torch.cat([tl.pack_conv_weights((torch.randn(64, 64, 3, 3, device='cuda') * 0.02).to(torch.bfloat16)) for _ in range(2)]).contiguous()
 b = torch.zeros(128, device='cuda')
 s = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+L.az_nn_resblock_scratch_bytes.restype = ctypes.c_size_t
+scr = torch.zeros(L.az_nn_resblock_scratch_bytes(), dtype=torch.uint8, device='cuda')
 for _ in range(4):
-    L.az_nn_resblock(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(b.data_ptr()), n, N, s)
+    L.az_nn_resblock(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(scr.data_ptr()), n, N, s)
 torch.cuda.synchronize()

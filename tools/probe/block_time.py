@@ -6,6 +6,7 @@ from azalea_b200 import _cabi, tower_layout as tl
 L = _cabi.lib()
 torch.manual_seed(0)
 P = lambda t: ctypes.c_void_p(t.data_ptr())
+SCR = torch.zeros(1 << 24, dtype=torch.uint8, device='cuda')     # >= az_nn_resblock_scratch_bytes()
 for n, N in ((11, 40960), (19, 5120), (11, 2048)):
     rows = L.az_nn_tower_rows(n, N)
     x = torch.zeros(rows, 64, device='cuda', dtype=torch.bfloat16)
@@ -21,7 +22,7 @@ for n, N in ((11, 40960), (19, 5120), (11, 2048)):
         L.az_nn_conv3x3(P(y), P(w[1]), P(b[1]), P(x), P(x), n, N, st)
 
     def one():
-        rc = L.az_nn_resblock(P(x), P(w12), P(b12), n, N, st)
+        rc = L.az_nn_resblock(P(x), P(w12), P(b12), P(SCR), n, N, st)
         assert rc == 0, (rc, L.az_last_cuda_error())
 
     for name, fn in (('two launches', two), ('fused', one)):
@@ -48,12 +49,12 @@ for flags, what in ((0, 'everything'), (2, 'no global stores (C)'), (4, 'no resi
                     (6, 'no global stores, no residual loads'), (8, 'no MMAs'), (14, 'barriers + TMEM + staging + copies only')):
     L.azb_set_debug(flags)
     for _ in range(3):
-        L.az_nn_resblock(P(x), P(w12), P(b12), n, N, st)
+        L.az_nn_resblock(P(x), P(w12), P(b12), P(SCR), n, N, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        L.az_nn_resblock(P(x), P(w12), P(b12), n, N, st)
+        L.az_nn_resblock(P(x), P(w12), P(b12), P(SCR), n, N, st)
     e1.record()
     torch.cuda.synchronize()
     print(f'debug {flags:2d} ({what}): {e0.elapsed_time(e1) / 20:.4f} ms', flush=True)
@@ -63,25 +64,25 @@ prof_lib = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libprof.so'
 if not os.path.exists(prof_lib):
     sys.exit(0)
 L = ctypes.CDLL(prof_lib)
-L.az_nn_resblock.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]
+L.az_nn_resblock.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p]
 L.azb_set_prof.argtypes = [ctypes.c_void_p]
 L.azb_set_prof.restype = None
 L.azb_set_debug.argtypes = [ctypes.c_int]
-prof = torch.zeros(2 * 7 * 8, dtype=torch.int64, device='cuda')
+prof = torch.zeros(2 * 8 * 8, dtype=torch.int64, device='cuda')
 names = {'epi': ['wait staging tile', 'wait mma_done', 'wait residual', 'tmem + math + stores', '', ''],
          'mma': ['wait in_full', '', 'wait blk_free', 'wait turn', 'issue + commit + pass', ''],
          'ldr': ['wait stage free', '', '', '', '', ''],
-         'rly': ['wait in_full', 'wait mma_done', '', '', '', ''], 'sto': ['wait out_done', 'wait y_free (P)', '', '', '', '']}
+         'rly': ['wait in_full', 'wait mma_done', '', '', '', ''], 'sto2': ['wait out_done', 'wait y_free (P)', '', '', '', '']}
 for flags in (0, 6, 14):
     L.azb_set_debug(flags)
     L.azb_set_prof(P(prof))
-    L.az_nn_resblock(P(x), P(w12), P(b12), n, N, st)
+    L.az_nn_resblock(P(x), P(w12), P(b12), P(SCR), n, N, st)
     torch.cuda.synchronize()
     L.azb_set_prof(None)
-    t = prof.cpu().view(2, 7, 8)
+    t = prof.cpu().view(2, 8, 8)
     print(f'--- debug {flags}: cycles per slab, cluster 0')
     for rank, rn in ((0, 'P'), (1, 'C')):
-        for role, (rname, kind) in enumerate((('epilogue g0', 'epi'), ('epilogue g1', 'epi'), ('mma even', 'mma'), ('mma odd', 'mma'), ('loader', 'ldr'), ('relay', 'rly'), ('storer', 'sto'))):
+        for role, (rname, kind) in enumerate((('epilogue g0', 'epi'), ('epilogue g1', 'epi'), ('mma even', 'mma'), ('mma odd', 'mma'), ('loader', 'ldr'), ('relay', 'rly'), ('storer even', 'sto2'), ('storer odd', 'sto2'))):
             row = t[rank, role]
             ns = max(int(row[7]), 1)
             per = ns if kind in ('ldr', 'rly', 'sto') else ns / 2      # these roles take every other slab

@@ -21,12 +21,13 @@
 #include "az_common.cuh"
 
 // Shared-memory staging of the root's children for the descents of a batch (the north star's
-// "hot tree levels").  Built, bit-exact, measured (profiles/r02_k_select_staged.txt): under ncu
-// 44 % less DRAM traffic (97 vs 175 MB per launch) and 17 % fewer warp instructions (1901 vs 2290
-// per descent), but in the running step the launch is 6.7 % SLOWER (0.164 vs 0.154 ms, tree-only
-// 1.54e8 vs 1.61e8 simulations/s, A/B on the same box): the root level is re-read from L1 anyway
-// (58 % L1 hit rate), and staging adds a serial prologue, a warp barrier per descent and a
-// write-back to a kernel that is bound by latency and issue, not by bytes.  Off by default.
+// "hot tree levels").  Built, bit-exact (the whole GPU suite passes with it), measured, and a
+// loss: at the same capture point ncu shows 144.9 vs 136.9 us, 1901 vs 1857 warp instructions
+// per descent and 97 vs 93 MB of DRAM traffic per launch (profiles/r02_k_select_staged.txt vs
+// r02_k_select.txt), and in the running step the launch is 6.7 % slower (0.164 vs 0.154 ms,
+// tree-only 1.54e8 vs 1.61e8 simulations/s, A/B on one box).  The root level is re-read from L1
+// anyway (69 % L1 hit rate), so staging saves nothing and adds a serial prologue, a warp
+// barrier per descent and a write-back to a kernel bound by latency and issue.  Off by default.
 #ifndef AZ_STAGE_ROOT
 #define AZ_STAGE_ROOT 0
 #endif

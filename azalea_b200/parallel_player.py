@@ -62,9 +62,20 @@ class Player:
             metrics['moves_per_game'] += float(np.sum(h['ply'][last] + 1))
             metrics['reward'] += float(np.sum(h['reward'][last]))
             examples.append(rows_to_dataframe(rows, self.board_size))
-        failed = self.sp.counters()['games_failed']
-        metrics['game_error'] = failed
+        self._report(metrics)
         return examples, metrics
+
+    def _report(self, metrics) -> None:
+        """Games dropped on SearchTreeFull (parallel_player.py:71-76) and
+        expansions skipped on a full pool half are never silent."""
+        import logging
+        cnt = self.sp.counters()
+        metrics['game_error'] = cnt['games_failed']
+        metrics['pool_skipped_expansions'] = cnt['pool_skipped_expansions']
+        if cnt['games_failed'] or cnt['pool_skipped_expansions']:
+            logging.warning('self-play: %d games dropped (tree full), %d expansions skipped on a full '
+                            'node pool -- raise nodes_per_game', cnt['games_failed'],
+                            cnt['pool_skipped_expansions'])
 
     def read_device(self, size: int):
         """Like ``read`` but the rows stay on the device (uint8
@@ -83,6 +94,7 @@ class Player:
                 total += count
         metrics['games'] = self.sp.counters()['games'] - games0
         metrics['moves_per_game'] = float(total)
+        self._report(metrics)
         return torch.cat(chunks), metrics
 
     def stop(self) -> None:

@@ -256,6 +256,43 @@ def test_pool_overflow_is_flagged_not_corrupting():
     assert float(v.sum()) > 0
 
 
+def test_soft_pool_full_skips_expansions_and_keeps_the_game():
+    """AZ_CFG_SOFT_POOL_FULL (the lockstep drivers' mode): when a game's pool
+    half is exhausted the expansion is skipped and counted, no status bit is
+    set, visits keep accumulating (every descent is still backed up), and the
+    game goes on: after the move the re-root compacts the pool and expansion
+    resumes.  Whole games finish with games_failed == 0."""
+    from azalea_b200 import Engine, LockstepSelfPlay, StubEvaluator
+    eng = Engine(4, 11, max_batch=10, nodes_per_game=2000, soft_pool_full=True)
+    eng.select_root(); eng.stub_eval(2); eng.expand_root()
+    for _ in range(40):
+        eng.select(10, 0.5); eng.stub_eval(2); eng.expand_backup()
+    assert (eng.status().cpu().numpy() == 0).all()
+    cnt = eng.counter_totals()
+    assert cnt['pool_skipped_expansions'] > 0
+    v, _, _, k, rnw, _ = eng.root_stats()
+    assert (k.cpu().numpy() == 121).all()
+    # 400 descents per game, duplicates inside a batch backed up once
+    assert (rnw[:, 0].cpu().numpy() >= 40).all() and (rnw[:, 0].cpu().numpy() <= 400).all()
+    # whole games on a pool far too small for a move's growth
+    sp = LockstepSelfPlay(StubEvaluator(2), num_games=32, board_size=7, simulations=120,
+                          search_batch_size=6, nodes_per_game=1500, cuda_graph=False)
+    for _ in range(60):
+        sp.step_move()
+    c = sp.counters()
+    assert c['pool_skipped_expansions'] > 0 and c['games_failed'] == 0 and c['games'] >= 32
+    assert (sp.eng.status().cpu().numpy() == 0).all()
+    rows = sp.harvest()
+    from azalea_b200.engine import decode_replay_rows
+    h, board, _ = decode_replay_rows(rows, 7)
+    game = oracle.Hex(7)
+    first = [i for i in range(len(h)) if h['game_id'][i] == h['game_id'][0]]
+    for i in first:                                 # a finished game is a legal game
+        assert (board[i] == game.board).all()
+        game.step(int(h['move'][i]))
+    assert game.result() == h['result'][first[0]]
+
+
 def test_reroot_compaction_preserves_subtree():
     """Re-rooting copies the kept subtree; searching on from it gives the
     same statistics as the reference, which keeps everything in place

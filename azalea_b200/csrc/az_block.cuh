@@ -98,12 +98,24 @@
 #define AZB_TC 2            // C: staging tiles
 #endif
 #define AZB_TMAX (AZB_TP > AZB_TC ? AZB_TP : AZB_TC)
+// How C reads the residual and writes its output:
+//   0  bulk-loaded residual ring + staging tile + bulk store (64 KB of shared-memory traffic per slab
+//      on top of the 136 KB of MMA operands and incoming y)
+//   1  (probe) straight from / to global memory by the epilogue threads, whole 128-byte lines per
+//      eight lanes, with an 8 x 8 register transpose (shuffles) between "lane = chunk" and "lane =
+//      row".  Bit-exact, no shared memory in C but operands and bias -- and slower: 0.628 ms per
+//      block against 0.572 (0.610 with six input stages): the two transposes are ~400 instructions
+//      per thread and slab, a group of four warps needs ~6000 cycles per slab, and the block ring
+//      waits for it (profiles/r02_fused_block.txt)
+#ifndef AZB_CDIRECT
+#define AZB_CDIRECT 0
+#endif
 #ifndef AZB_PROF
 #define AZB_PROF 0          // 1: probe build with per-role cycle accounting (tools/probe/block_time.py)
 #endif
 #define AZB_SMAX (AZB_SX > AZB_SY ? AZB_SX : AZB_SY)
 #define AZB_SMEM_P (AZT_WBYTES + AZB_SX * AZT_CHUNK_BYTES + (AZB_P_ASYNC ? 0 : AZB_TP) * AZT_OUT_BYTES)
-#define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_SR + AZB_TC) * AZT_OUT_BYTES)
+#define AZB_SMEM_C (AZT_WBYTES + AZB_SY * AZT_CHUNK_BYTES + (AZB_CDIRECT ? 0 : AZB_SR + AZB_TC) * AZT_OUT_BYTES)
 #define AZB_SMEM_BYTES (AZB_SMEM_P > AZB_SMEM_C ? AZB_SMEM_P : AZB_SMEM_C)
 static_assert(AZB_SY <= AZB_R, "bar_y_free is sized for the scratch ring");
 static_assert(AZB_SX <= 8 && AZB_SY <= 8, "stage reuse is tracked through the 8 MMA-retired barriers");
@@ -194,6 +206,44 @@ __device__ __forceinline__ void azb_stg_sector(void *p, const uint4 &lo, const u
                    "l"((unsigned long long)hi.z | ((unsigned long long)hi.w << 32)) : "memory");
 }
 
+__device__ __forceinline__ uint4 azb_ldg16(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void azb_stg16(void *p, const uint4 &v)
+{
+    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// 8 x 8 transpose of 16-byte elements over the eight lanes of a lane group: element r[i] of lane
+// s (s = lane & 7) <-> element r[s] of lane i.  Three butterfly stages; its own inverse.
+template <int BIT>
+__device__ __forceinline__ void azb_transpose_stage(uint4 (&r)[8], const bool up)
+{
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i & BIT) continue;
+        const uint4 a = r[i], b = r[i | BIT];
+        uint4 snd = up ? a : b, rcv;
+        rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, BIT);
+        rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, BIT);
+        rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, BIT);
+        rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, BIT);
+        r[i] = up ? rcv : a;
+        r[i | BIT] = up ? b : rcv;
+    }
+}
+
+__device__ __forceinline__ void azb_transpose8(uint4 (&r)[8], const int lane)
+{
+    azb_transpose_stage<1>(r, (lane & 1) != 0);
+    azb_transpose_stage<2>(r, (lane & 2) != 0);
+    azb_transpose_stage<4>(r, (lane & 4) != 0);
+}
+
 // probe: accumulate the cycles spent in `stmt` into slot k of this CTA's profile row
 #define AZB_TIMED(k, stmt)                                                          \
     do {                                                                            \
@@ -238,7 +288,8 @@ k_resblock(const azb_params p)
             azt_mbar_init(&bar_res_empty[i], 8);        // the eight warps of the group that read it
         }
         for (int i = 0; i < 8; i++) azt_mbar_init(&bar_mma_done[i], 1);
-        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], 8);    // one arrival per warp of a group
+        // one arrival per warp of the group that drained the block
+        for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], AZB_CDIRECT && !isP ? 4 : 8);
         for (int i = 0; i < AZB_R; i++) { azt_mbar_init(&bar_y_free[i], 1); azt_mbar_init(&bar_y_ready[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;");
         // C arms every stage of its input ring for the first slab P will copy into it
@@ -316,7 +367,7 @@ k_resblock(const azb_params p)
                 azb_bulk_s2s(azb_remote(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, 1),
                              s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES, azb_remote(&bar_in_full[st], 1));
             }
-        } else if (!isP && lane == 0) {
+        } else if (!isP && lane == 0 && !AZB_CDIRECT) {
             // C: finished output slab -> global memory, in place
             for (int j = sw_; j < nslabs; j += AZB_STORERS) {
                 const int sb = j % AZB_TC;
@@ -385,7 +436,7 @@ k_resblock(const azb_params p)
                     azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES, p.x + (size_t)((q0 + j) * 128) * AZT_ROW,
                                  AZT_CHUNK_BYTES, &bar_in_full[st]);
                 }
-            } else if (!(p.debug & 4)) {
+            } else if (!(p.debug & 4) && !AZB_CDIRECT) {
                 // the residual: the block's own input slab, again (L2: P has just read it)
                 for (int j = 0; j < nslabs; j++) {
                     const int sr = j % AZB_SR;
@@ -463,6 +514,77 @@ k_resblock(const azb_params p)
                 else asm volatile("bar.arrive 3, 64;" ::: "memory");
             }
             if (prof_on) prof_acc[4] += clock64() - ti_;
+        }
+    } else if (AZB_CDIRECT && !isP) {
+        // ------------------------------------------- epilogue of C, direct --
+        // Four groups of four warps on output slabs j = group (mod 4); a warp owns ALL 64 channels of
+        // the 32 rows of its TMEM lane quadrant: thread = TMEM lane = row l.  The residual comes from
+        // and the result goes to global memory as whole lines: in access i of 8 the eight lanes of
+        // lane group G cover the 128 bytes of row 8 G + i (lane k the chunk at position k ^ i, which
+        // is LOGICAL chunk k of that row: the swizzle is in the address), and a register transpose
+        // turns "lane k holds chunk k of rows 8 G + 0..7" into "lane k holds chunks 0..7 of row
+        // 8 G + k" and back.  No shared memory but the bias.
+        const int grp = warp >> 2, wq = warp & 3;
+        const int l = wq * 32 + lane, G = lane >> 3, k = lane & 7;
+        const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
+        const uint32_t keep = real ? 0xffffffffu : 0u;
+        for (int j = grp, y = grp % n; j < nslabs; j += 4, y = (y + 4) % n) {
+            uint8_t *rows8 = p.x + (size_t)(AZT_HALO + (q0 + j) * 128 + wq * 32 + 8 * G) * AZT_ROW;
+            uint4 R[8];
+            if (!(p.debug & 4)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) R[i] = azb_ldg16(rows8 + i * AZT_ROW + ((k ^ i) << 4));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) R[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
+            const int last = y + 1 < n ? j + 1 : j;
+            AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            const long long tb_ = prof_on ? clock64() : 0;
+            azb_transpose8(R, lane);                    // -> R[c] = logical chunk c of this thread's row
+            const int blk = AZB_RING(j);
+            const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u;
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                uint32_t acc[16];
+                AZT_TMEM_LD16(acc, ta + h * 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;");
+                azt_tmem_zero16(ta + h * 16);       // retire: zero for the block's next output slab
+#pragma unroll
+                for (int g = 0; g < 2; g++) {
+                    const int c8 = h * 2 + g;                       // 8-channel chunk of the row
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8 + 4]);
+                    float f[8];
+                    f[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(acc[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(acc[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(acc[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(acc[g * 8 + 7]) + b1.w;
+                    const uint32_t rw[4] = {R[c8].x, R[c8].y, R[c8].z, R[c8].w};
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        f[2 * q] += __uint_as_float(rw[q] << 16);
+                        f[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
+                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
+                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
+                    }
+                    R[c8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            }
+            // hand the ring block back
+            asm volatile("tcgen05.wait::st.sync.aligned;");
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) azt_mbar_arrive(&bar_blk_free[blk]);
+            azb_transpose8(R, lane);                    // -> R[i] = logical chunk k of row 8 G + i
+            if (!(p.debug & 2)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) azb_stg16(rows8 + i * AZT_ROW + ((k ^ i) << 4), R[i]);
+            }
+            if (prof_on) prof_acc[3] += clock64() - tb_;
         }
     } else {
         // ----------------------------------------------------- epilogue --

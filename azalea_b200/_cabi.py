@@ -118,6 +118,7 @@ def lib():
     L.az_nn_tower_rows.restype = C.c_int64
     L.az_nn_conv3x3.argtypes = [vp, vp, f32p, vp, vp, C.c_int, C.c_int64, vp]
     L.az_nn_resblock.argtypes = [vp, vp, f32p, vp, C.c_int, C.c_int64, vp]
+    L.az_nn_resblocks.argtypes = [vp, vp, f32p, vp, C.c_int, C.c_int64, C.c_int, vp]
     L.az_nn_resblock_scratch_bytes.restype = C.c_size_t
     L.az_noise_sample.argtypes = [eng, C.c_float, C.c_int, C.c_int, f32p, vp]
     L.az_play_commit.argtypes = [eng, C.POINTER(AzPlayParams), i32p, vp]

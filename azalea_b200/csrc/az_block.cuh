@@ -129,13 +129,16 @@ static_assert(AZB_TC % 2 == 0 && AZB_SR % 2 == 0 && (AZB_P_ASYNC || AZB_TP % 2 =
               "rings shared by the two epilogue groups must have an even number of entries");
 static_assert(!AZB_P_ASYNC || AZB_SY % 2 == 0, "st.async variant: a stage of C's ring belongs to one epilogue group of P");
 
+#define AZB_MAXPASS 8       // residual blocks one launch can chain (their biases sit in shared memory)
+
 struct azb_params {
     uint8_t *x;             // activations, slab layout, pre-swizzled; updated in place
-    const uint8_t *w;       // [2 layers][3 dx][192 = dy*64 + c_out][128 B] pre-swizzled weights
-    const float *bias;      // [2][64]
+    const uint8_t *w;       // [passes][2 layers][3 dx][192 = dy*64 + c_out][128 B] pre-swizzled weights
+    const float *bias;      // [passes][2][64]
     int n;                  // board size
     int bpg;                // boards per group = 128 / (n+1)
     long long groups;       // board groups
+    int passes;             // residual blocks to apply, one after the other (1 .. AZB_MAXPASS)
     uint8_t *scratch;       // AZB_VIA_L2: [clusters][AZB_R][16 KB] hand-over ring in global memory
     unsigned long long *prof;   // probe only: per-role wait cycles of cluster 0 ([rank][32]) or NULL
     int debug;              // probe only (tools/probe/block_time.py): 2 = C skips its global stores,
@@ -196,6 +199,19 @@ __device__ __forceinline__ void azb_wait_cluster(uint64_t *bar, uint32_t parity)
     azt_mbar_wait(bar, parity);
 }
 
+// The count of output slabs whose bulk store to global memory has COMPLETED, kept in both CTAs'
+// shared memory by C's storer (chained blocks only: the next block's loads of a slab wait for it).
+__device__ __forceinline__ void azb_publish(volatile uint32_t *own, uint32_t v)
+{
+    *own = v;
+    asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(azb_remote((const void *)own, 0)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void azb_wait_stored(const volatile uint32_t *cnt, uint32_t need)
+{
+    while (*cnt < need) asm volatile("nanosleep.u32 64;");
+}
+
 // one 32-byte sector of a row: 16-byte chunks lo | hi
 __device__ __forceinline__ void azb_stg_sector(void *p, const uint4 &lo, const uint4 &hi)
 {
@@ -251,6 +267,18 @@ __device__ __forceinline__ void azb_transpose8(uint4 (&r)[8], const int lane)
         else { stmt; }                                                              \
     } while (0)
 
+// A role's position in the chained sequence of slabs: t = pass * nslabs + j runs over all the
+// passes (rings, barrier phases and the TMEM ring continue across a pass boundary; nslabs is a
+// multiple of the board size, so the board row of slab t is t % n), j addresses global memory.
+struct azb_pos {
+    int t, j, pass;
+    __device__ __forceinline__ void advance(int step, int nslabs)
+    {
+        t += step; j += step;
+        while (j >= nslabs) { j -= nslabs; pass++; }
+    }
+};
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(AZB_THREADS, 1)
 k_resblock(const azb_params p)
 {
@@ -265,12 +293,13 @@ k_resblock(const azb_params p)
     __shared__ uint64_t bar_w, bar_in_full[AZB_SMAX];
     __shared__ uint64_t bar_out_empty[AZB_TMAX], bar_out_done[AZB_TMAX];    // staging tiles
     __shared__ uint64_t bar_res_full[AZB_SR], bar_res_empty[AZB_SR];        // C: residual ring
-    __shared__ uint64_t bar_mma_done[8];            // MMA(j) retired, by j & 7
+    __shared__ uint64_t bar_mma_done[8];            // MMA(t) retired, by t & 7
     __shared__ uint64_t bar_blk_free[AZT_BLOCKS];   // ring block read, zeroed and free for its next output slab
     __shared__ uint64_t bar_y_free[AZB_R];          // P: stage of C's ring / scratch slot consumed (arrived by C)
     __shared__ uint64_t bar_y_ready[AZB_R];         // C (AZB_VIA_L2): scratch slot written (arrived by P)
     __shared__ uint32_t tmem_holder;
-    __shared__ __align__(16) float s_bias[AZT_C];
+    __shared__ volatile uint32_t s_stored;          // output slabs (index t) whose store has completed
+    __shared__ __align__(16) float s_bias[AZB_MAXPASS * AZT_C];     // this CTA's layer of every pass
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool prof_on = AZB_PROF && p.prof != nullptr && (blockIdx.x >> 1) == 0 && lane == 0;
@@ -291,12 +320,14 @@ k_resblock(const azb_params p)
         // one arrival per warp of the group that drained the block
         for (int i = 0; i < AZT_BLOCKS; i++) azt_mbar_init(&bar_blk_free[i], AZB_CDIRECT && !isP ? 4 : 8);
         for (int i = 0; i < AZB_R; i++) { azt_mbar_init(&bar_y_free[i], 1); azt_mbar_init(&bar_y_ready[i], 1); }
+        s_stored = 0;
         asm volatile("fence.mbarrier_init.release.cluster;");
         // C arms every stage of its input ring for the first slab P will copy into it
         if (!isP && !AZB_VIA_L2)
             for (int i = 0; i < AZB_SY; i++) azt_mbar_expect_tx(&bar_in_full[i], AZT_OUT_BYTES);
     }
-    if (tid < AZT_C) s_bias[tid] = p.bias[rank * AZT_C + tid];
+    for (int i = tid; i < p.passes * AZT_C; i += AZB_THREADS)
+        s_bias[i] = p.bias[((i / AZT_C) * 2 + rank) * AZT_C + (i % AZT_C)];
     if (!isP) {
         // P only ever writes the 128 slab rows of a stage; the 8 rows in front of them are the
         // zero rows every slab is preceded by, the 8 rows behind feed masked outputs only
@@ -313,13 +344,14 @@ k_resblock(const azb_params p)
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_holder;
 
-    // this cluster's contiguous range of groups -> slabs [q0, q0 + nslabs), local index j = q - q0;
-    // board row y = j % n
+    // this cluster's contiguous range of groups -> slabs [q0, q0 + nslabs) of every pass; NT slabs
+    // in all, t = pass * nslabs + j; board row y = t % n
     const int n = p.n;
     const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
     const long long g0 = p.groups * cid / ncl, g1 = p.groups * (cid + 1) / ncl;
     const long long q0 = g0 * n;
     const int nslabs = (int)((g1 - g0) * n);
+    const int NT = nslabs * p.passes;
 #define AZB_RING(u) ((8 - ((u) & 7)) & 7)
 
     if (warp < 16) {
@@ -343,12 +375,12 @@ k_resblock(const azb_params p)
         // with the MMAs running the kernel is bound elsewhere and the extra warp costs 1 %.
         const int sw_ = warp - 20;          // AZB_STORERS == 1: warp 20 takes every slab
         if (isP && lane == 0 && AZB_VIA_L2) {
-            // P: finished y slab: staging tile -> slot j % AZB_R of the cluster's scratch ring
+            // P: finished y slab: staging tile -> slot t % AZB_R of the cluster's scratch ring
             uint8_t *ring = p.scratch + (size_t)cid * AZB_R * AZT_OUT_BYTES;
-            for (int j = sw_; j < nslabs; j += AZB_STORERS) {
-                const int sb = j % AZB_TP, ss = j % AZB_R;
-                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1));
-                if (j >= AZB_R) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[ss], ((j / AZB_R) & 1) ^ 1));
+            for (int t = sw_; t < NT; t += AZB_STORERS) {
+                const int sb = t % AZB_TP, ss = t % AZB_R;
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (t / AZB_TP) & 1));
+                if (t >= AZB_R) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[ss], ((t / AZB_R) & 1) ^ 1));
                 azt_bulk_s2g(ring + (size_t)ss * AZT_OUT_BYTES, s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // the tile is free as soon as the store has READ it ...
@@ -360,60 +392,87 @@ k_resblock(const azb_params p)
             }
         } else if (isP && lane == 0 && !AZB_P_ASYNC && sw_ == 0) {
             // P: finished y slab: staging tile -> rows 8..135 of stage st of C's input ring
-            for (int j = 0; j < nslabs; j++) {
-                const int sb = j % AZB_TP, st = j % AZB_SY;
-                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TP) & 1));
-                if (j >= AZB_SY) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1));
+            for (int t = 0; t < NT; t++) {
+                const int sb = t % AZB_TP, st = t % AZB_SY;
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (t / AZB_TP) & 1));
+                if (t >= AZB_SY) AZB_TIMED(1, azb_wait_cluster(&bar_y_free[st], ((t / AZB_SY) & 1) ^ 1));
                 azb_bulk_s2s(azb_remote(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, 1),
                              s_out + sb * AZT_OUT_BYTES, AZT_OUT_BYTES, azb_remote(&bar_in_full[st], 1));
             }
         } else if (!isP && lane == 0 && !AZB_CDIRECT) {
             // C: finished output slab -> global memory, in place
-            for (int j = sw_; j < nslabs; j += AZB_STORERS) {
-                const int sb = j % AZB_TC;
-                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (j / AZB_TC) & 1));
+            azb_pos at = {sw_, sw_, 0};
+            at.advance(0, nslabs);
+            for (; at.t < NT; at.advance(AZB_STORERS, nslabs)) {
+                const int sb = at.t % AZB_TC;
+                AZB_TIMED(0, azt_mbar_wait(&bar_out_done[sb], (at.t / AZB_TC) & 1));
                 if (!(p.debug & 2))
-                    azt_bulk_s2g(p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
+                    azt_bulk_s2g(p.x + (size_t)(AZT_HALO + (q0 + at.j) * 128) * AZT_ROW, s_out + sb * AZT_OUT_BYTES,
                                  AZT_OUT_BYTES);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 // hand the tile back as soon as the store has READ it (the write to global
                 // memory goes on): each epilogue group has one tile
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 azt_mbar_arrive(&bar_out_empty[sb]);
+                if (p.passes > 1 && AZB_STORERS == 1) {
+                    // chained blocks: the next pass loads these slabs again (P as its input, C as
+                    // its residual) once their stores have COMPLETED.  All stores but this one
+                    // have (the last slab of a pass: this one too); say so in both CTAs.
+                    if (at.j + 1 == nslabs) {
+                        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        azb_publish(&s_stored, (uint32_t)at.t + 1u);
+                    } else {
+                        asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                        azb_publish(&s_stored, (uint32_t)at.t);
+                    }
+                }
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
     } else if (warp == 19) {
-        // --------------------------------------------------------- relay (C) --
-        if (!isP && lane == 0 && AZB_VIA_L2) {
+        // ------------------------ relay (C, lane 0) / weights (both, lane 1) --
+        if (lane == 1) {
+            // both CTAs: this layer's weights, pass after pass.  The thread follows EVERY slab's
+            // "MMA retired" barrier in order (a parity wait is only sound one phase away), and
+            // loads the next pass's weights when the last slab of a pass has retired.
+            const uint8_t *w = p.w + (size_t)rank * AZT_WBYTES;
+            for (int pass = 0; pass < p.passes; pass++) {
+                if (pass > 0)
+                    for (int t = (pass - 1) * nslabs; t < pass * nslabs; t++)
+                        azt_mbar_wait(&bar_mma_done[t & 7], (t >> 3) & 1);
+                azt_mbar_expect_tx(&bar_w, AZT_WBYTES);
+                for (int tp = 0; tp < 9; tp++)
+                    azt_bulk_g2s(s_w + tp * 8192, w + (size_t)(pass * 2) * AZT_WBYTES + tp * 8192, 8192, &bar_w);
+            }
+        } else if (!isP && lane == 0 && AZB_VIA_L2) {
             // C: y loader: scratch slot -> rows 8..135 of stage st of the input ring (an L2 hit), and,
             // two slabs later, the slot back to P
             const uint8_t *ring = p.scratch + (size_t)cid * AZB_R * AZT_OUT_BYTES;
-            for (int j = 0; j < nslabs + 2; j++) {
-                if (j < nslabs) {
-                    const int ss = j % AZB_R, st = j % AZB_SY;
-                    AZB_TIMED(0, azb_wait_cluster(&bar_y_ready[ss], (j / AZB_R) & 1));
-                    if (j >= AZB_SY) AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[(j - AZB_SY) & 7], ((j - AZB_SY) >> 3) & 1));
+            for (int t = 0; t < NT + 2; t++) {
+                if (t < NT) {
+                    const int ss = t % AZB_R, st = t % AZB_SY;
+                    AZB_TIMED(0, azb_wait_cluster(&bar_y_ready[ss], (t / AZB_R) & 1));
+                    if (t >= AZB_SY) AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[(t - AZB_SY) & 7], ((t - AZB_SY) >> 3) & 1));
                     azt_mbar_expect_tx(&bar_in_full[st], AZT_OUT_BYTES);
                     azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES + 8 * AZT_ROW, ring + (size_t)ss * AZT_OUT_BYTES,
                                  AZT_OUT_BYTES, &bar_in_full[st]);
                 }
-                if (j >= 2 && j - 2 + AZB_R < nslabs) {
-                    const int k = j - 2;
+                if (t >= 2 && t - 2 + AZB_R < NT) {
+                    const int k = t - 2;
                     azt_mbar_wait(&bar_in_full[k % AZB_SY], (k / AZB_SY) & 1);
                     azb_remote_arrive(azb_remote(&bar_y_free[k % AZB_R], 0));
                 }
             }
         } else if (!isP && lane == 0) {
-            for (int j = 0; j <= nslabs; j++) {
-                if (j < nslabs && !AZB_P_ASYNC) {
-                    // slab j has landed in C: P's staging tile that held it may be rewritten
-                    AZB_TIMED(0, azb_wait_cluster(&bar_in_full[j % AZB_SY], (j / AZB_SY) & 1));
-                    azb_remote_arrive(azb_remote(&bar_out_empty[j % AZB_TP], 0));
+            for (int t = 0; t <= NT; t++) {
+                if (t < NT && !AZB_P_ASYNC) {
+                    // slab t has landed in C: P's staging tile that held it may be rewritten
+                    AZB_TIMED(0, azb_wait_cluster(&bar_in_full[t % AZB_SY], (t / AZB_SY) & 1));
+                    azb_remote_arrive(azb_remote(&bar_out_empty[t % AZB_TP], 0));
                 }
-                if (j >= 1 && j - 1 + AZB_SY < nslabs) {
-                    // MMA2(j-1) has read its stage: arm it for its next slab, then let P copy that in
-                    const int k = j - 1;
+                if (t >= 1 && t - 1 + AZB_SY < NT) {
+                    // MMA2(t-1) has read its stage: arm it for its next slab, then let P copy that in
+                    const int k = t - 1;
                     AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[k & 7], (k >> 3) & 1));
                     azt_mbar_expect_tx(&bar_in_full[k % AZB_SY], AZT_OUT_BYTES);
                     azb_remote_arrive(azb_remote(&bar_y_free[k % AZB_SY], 0));
@@ -422,27 +481,30 @@ k_resblock(const azb_params p)
         }
     } else if (warp == 18) {
         // ------------------------------------------------------------ loader --
-        if (lane == 0) {
-            azt_mbar_expect_tx(&bar_w, AZT_WBYTES);
-            const uint8_t *w = p.w + (size_t)rank * AZT_WBYTES;
-            for (int t = 0; t < 9; t++) azt_bulk_g2s(s_w + t * 8192, w + t * 8192, 8192, &bar_w);
-            if (isP) {
-                for (int j = 0; j < nslabs; j++) {
-                    const int st = j % AZB_SX;
-                    // the stage is free once the MMAs of the slab that used it last have retired
-                    if (j >= AZB_SX) AZB_TIMED(0, azt_mbar_wait(&bar_mma_done[(j - AZB_SX) & 7], ((j - AZB_SX) >> 3) & 1));
-                    // slab rows plus 8 rows on each side: global rows [128 q, 128 q + 144)
-                    azt_mbar_expect_tx(&bar_in_full[st], AZT_CHUNK_BYTES);
-                    azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES, p.x + (size_t)((q0 + j) * 128) * AZT_ROW,
-                                 AZT_CHUNK_BYTES, &bar_in_full[st]);
-                }
-            } else if (!(p.debug & 4) && !AZB_CDIRECT) {
-                // the residual: the block's own input slab, again (L2: P has just read it)
-                for (int j = 0; j < nslabs; j++) {
-                    const int sr = j % AZB_SR;
-                    AZB_TIMED(0, azt_mbar_wait(&bar_res_empty[sr], ((j / AZB_SR) & 1) ^ 1));
+        if (lane == 0 && isP) {
+            azb_pos at = {0, 0, 0};
+            for (; at.t < NT; at.advance(1, nslabs)) {
+                const int st = at.t % AZB_SX;
+                // the stage is free once the MMAs of the slab that used it last have retired
+                if (at.t >= AZB_SX) AZB_TIMED(0, azt_mbar_wait(&bar_mma_done[(at.t - AZB_SX) & 7], ((at.t - AZB_SX) >> 3) & 1));
+                // chained blocks: the slab is the previous pass's output
+                if (at.pass > 0) AZB_TIMED(1, azb_wait_stored(&s_stored, (uint32_t)(at.t - nslabs) + 1u));
+                // slab rows plus 8 rows on each side: global rows [128 q, 128 q + 144)
+                azt_mbar_expect_tx(&bar_in_full[st], AZT_CHUNK_BYTES);
+                azt_bulk_g2s(s_in + st * AZT_CHUNK_BYTES, p.x + (size_t)((q0 + at.j) * 128) * AZT_ROW,
+                             AZT_CHUNK_BYTES, &bar_in_full[st]);
+            }
+        } else if (lane == 0) {
+            // C: the residual: the block's own input slab, again (L2: P has just read it)
+            if (!(p.debug & 4) && !AZB_CDIRECT) {
+                azb_pos at = {0, 0, 0};
+                for (; at.t < NT; at.advance(1, nslabs)) {
+                    const int sr = at.t % AZB_SR;
+                    AZB_TIMED(0, azt_mbar_wait(&bar_res_empty[sr], ((at.t / AZB_SR) & 1) ^ 1));
+                    // chained blocks: the slab is this CTA's own output of the previous pass
+                    if (at.pass > 0) azb_wait_stored(&s_stored, (uint32_t)(at.t - nslabs) + 1u);
                     azt_mbar_expect_tx(&bar_res_full[sr], AZT_OUT_BYTES);
-                    azt_bulk_g2s(s_res + sr * AZT_OUT_BYTES, p.x + (size_t)(AZT_HALO + (q0 + j) * 128) * AZT_ROW,
+                    azt_bulk_g2s(s_res + sr * AZT_OUT_BYTES, p.x + (size_t)(AZT_HALO + (q0 + at.j) * 128) * AZT_ROW,
                                  AZT_OUT_BYTES, &bar_res_full[sr]);
                 }
             }
@@ -452,22 +514,26 @@ k_resblock(const azb_params p)
         // Warp 16 issues the even slabs, warp 17 the odd ones (az_tower.cuh).  The turn passes
         // through named barriers 3 (-> even) and 4 (-> odd).
         const int w = warp - 16;
-        azt_mbar_wait(&bar_w, 0);
         const uint64_t db_base = azt_desc(azt_smem(s_w));
-        if (w == 1 && nslabs > 0) asm volatile("bar.arrive 3, 64;" ::: "memory");   // slab 0 has the first turn
-        for (int j = w, y = w % n; j < nslabs; j += 2, y = (y + 2) % n) {
-            const int st = j % S;
-            // input slab j feeds output slabs j+1 (dy 0), j (dy 1), j-1 (dy 2) of the same group
+        if (w == 1 && NT > 0) asm volatile("bar.arrive 3, 64;" ::: "memory");   // slab 0 has the first turn
+        int wpass = -1;                     // pass whose weights this warp has waited for
+        azb_pos at = {w, w, 0};
+        at.advance(0, nslabs);
+        for (int y = w % n; at.t < NT; at.advance(2, nslabs), y = (y + 2) % n) {
+            const int t = at.t, st = t % S;
+            // input slab t feeds output slabs t+1 (dy 0), t (dy 1), t-1 (dy 2) of the same group
             const int dy0 = y + 1 < n ? 0 : 1, dy1 = y > 0 ? 2 : 1;
-            const int top = j + 1 - dy0;
+            const int top = t + 1 - dy0;
             // highest output slab entered by the slabs before this one
-            const int entered = j == 0 ? -1 : (y == 0 ? j - 1 : j);
-            AZB_TIMED(0, azb_wait_cluster(&bar_in_full[st], (j / S) & 1));
+            const int entered = t == 0 ? -1 : (y == 0 ? t - 1 : t);
+            AZB_TIMED(0, azb_wait_cluster(&bar_in_full[st], (t / S) & 1));
+            // this pass's weights (the other warp's MMAs of the last pass retire before they are replaced)
+            while (wpass < at.pass) { wpass++; azt_mbar_wait(&bar_w, wpass & 1); }
             // st.async variant: the slab was not written by the async proxy the tensor core reads through
             if (AZB_P_ASYNC && !isP) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            // a block entered for a new output slab t: its previous tenant t-8 must have been retired
-            for (int t = entered + 1; t <= top; t++)
-                if (t >= 8) AZB_TIMED(2, azt_mbar_wait(&bar_blk_free[AZB_RING(t)], ((t >> 3) - 1) & 1));
+            // a block entered for a new output slab u: its previous tenant u-8 must have been retired
+            for (int u = entered + 1; u <= top; u++)
+                if (u >= 8) AZB_TIMED(2, azt_mbar_wait(&bar_blk_free[AZB_RING(u)], ((u >> 3) - 1) & 1));
             const int blk = AZB_RING(top), nb = dy1 - dy0 + 1;
             const int first = nb < 8 - blk ? nb : 8 - blk, second = nb - first;     // split where the ring wraps
             const uint32_t d0 = tmem + blk * 64, i0 = AZT_IDESC(first), i1 = AZT_IDESC(second);
@@ -475,7 +541,7 @@ k_resblock(const azb_params p)
             const uint64_t da0 = azt_desc(azt_smem(s_in + st * AZT_CHUNK_BYTES) + 7 * AZT_ROW);    // row l-1 of the slab
             const uint64_t db0 = db_base + (uint64_t)(dy0 * 64 * (AZT_ROW / 16));
             const uint64_t db1 = db0 + (uint64_t)(first * 64 * (AZT_ROW / 16));
-            // take the turn: the other warp has issued slab j-1
+            // take the turn: the other warp has issued slab t-1
             const long long tt_ = prof_on ? clock64() : 0;
             if (w == 0) asm volatile("bar.sync 3, 64;" ::: "memory");
             else asm volatile("bar.sync 4, 64;" ::: "memory");
@@ -505,11 +571,11 @@ k_resblock(const azb_params p)
                 }
                 // one commit per slab: output slabs wait for it, and so does the input stage
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             ::"r"(azt_smem(&bar_mma_done[j & 7])) : "memory");
+                             ::"r"(azt_smem(&bar_mma_done[t & 7])) : "memory");
             }
             __syncwarp();
             asm volatile("tcgen05.fence::before_thread_sync;");
-            if (j + 1 < nslabs) {
+            if (t + 1 < NT) {
                 if (w == 0) asm volatile("bar.arrive 4, 64;" ::: "memory");
                 else asm volatile("bar.arrive 3, 64;" ::: "memory");
             }
@@ -517,13 +583,13 @@ k_resblock(const azb_params p)
         }
     } else if (AZB_CDIRECT && !isP) {
         // ------------------------------------------- epilogue of C, direct --
-        // Four groups of four warps on output slabs j = group (mod 4); a warp owns ALL 64 channels of
-        // the 32 rows of its TMEM lane quadrant: thread = TMEM lane = row l.  The residual comes from
-        // and the result goes to global memory as whole lines: in access i of 8 the eight lanes of
-        // lane group G cover the 128 bytes of row 8 G + i (lane k the chunk at position k ^ i, which
-        // is LOGICAL chunk k of that row: the swizzle is in the address), and a register transpose
-        // turns "lane k holds chunk k of rows 8 G + 0..7" into "lane k holds chunks 0..7 of row
-        // 8 G + k" and back.  No shared memory but the bias.
+        // (probe, single pass only.)  Four groups of four warps on output slabs t = group (mod 4); a
+        // warp owns ALL 64 channels of the 32 rows of its TMEM lane quadrant: thread = TMEM lane = row
+        // l.  The residual comes from and the result goes to global memory as whole lines: in access
+        // i of 8 the eight lanes of lane group G cover the 128 bytes of row 8 G + i (lane k the chunk
+        // at position k ^ i, which is LOGICAL chunk k of that row: the swizzle is in the address), and
+        // a register transpose turns "lane k holds chunk k of rows 8 G + 0..7" into "lane k holds
+        // chunks 0..7 of row 8 G + k" and back.  No shared memory but the bias.
         const int grp = warp >> 2, wq = warp & 3;
         const int l = wq * 32 + lane, G = lane >> 3, k = lane & 7;
         const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
@@ -588,7 +654,7 @@ k_resblock(const azb_params p)
         }
     } else {
         // ----------------------------------------------------- epilogue --
-        // group = warp >> 3 takes the output slabs j = group (mod 2); inside a group a warp
+        // group = warp >> 3 takes the output slabs t = group (mod 2); inside a group a warp
         // owns 32 channels (half) of the 32 rows its TMEM lane quadrant holds:
         // thread = TMEM lane = row l of the slab
         const int grp = warp >> 3, half = (warp >> 2) & 1, wq = warp & 3;
@@ -596,14 +662,17 @@ k_resblock(const azb_params p)
         const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
         const uint32_t keep = real ? 0xffffffffu : 0u;
         const int sw = l & 7;                                       // == R & 7 (8 + 128 q + l)
-        for (int j = grp, y = grp % n; j < nslabs; j += 2, y = (y + 2) % n) {
-            const int sb = j % T;
+        azb_pos at = {grp, grp, 0};
+        at.advance(0, nslabs);
+        for (int y = grp % n; at.t < NT; at.advance(2, nslabs), y = (y + 2) % n) {
+            const int t = at.t, sb = t % T;
+            const float *bias = s_bias + at.pass * AZT_C;
             uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
             uint4 rv[4];
             if (!isP && !(p.debug & 4)) {
                 // this thread's row and channels of the residual slab, from the bulk-loaded ring
-                const int sr = j % AZB_SR;
-                AZB_TIMED(2, azt_mbar_wait(&bar_res_full[sr], (j / AZB_SR) & 1));
+                const int sr = t % AZB_SR;
+                AZB_TIMED(2, azt_mbar_wait(&bar_res_full[sr], (t / AZB_SR) & 1));
                 const uint4 *rrow = reinterpret_cast<const uint4 *>(s_res + sr * AZT_OUT_BYTES + l * AZT_ROW);
 #pragma unroll
                 for (int c = 0; c < 4; c++) rv[c] = rrow[(half * 4 + c) ^ sw];
@@ -623,21 +692,21 @@ k_resblock(const azb_params p)
             uint32_t ybase = 0, ybar = 0;
             if (AZB_P_ASYNC && isP) {
                 // row 8 + l of stage st of C's ring, once MMA2 has retired the slab that was there
-                const int st = j % AZB_SY;
-                if (lane == 0) AZB_TIMED(0, azb_wait_cluster(&bar_y_free[st], ((j / AZB_SY) & 1) ^ 1));
+                const int st = t % AZB_SY;
+                if (lane == 0) AZB_TIMED(0, azb_wait_cluster(&bar_y_free[st], ((t / AZB_SY) & 1) ^ 1));
                 __syncwarp();
                 ybase = azb_remote(s_in + st * AZT_CHUNK_BYTES + (8 + l) * AZT_ROW, 1);
                 ybar = azb_remote(&bar_in_full[st], 1);
             } else {
                 // the staging tile must have been drained by the copy / store that used it last
-                AZB_TIMED(0, azb_wait_cluster(&bar_out_empty[sb], ((j / T) & 1) ^ 1));
+                AZB_TIMED(0, azb_wait_cluster(&bar_out_empty[sb], ((t / T) & 1) ^ 1));
             }
-            // output slab j is complete once MMA(j+1) retired (MMA(j) for the last board row)
-            const int last = y + 1 < n ? j + 1 : j;
+            // output slab t is complete once MMA(t+1) retired (MMA(t) for the last board row)
+            const int last = y + 1 < n ? t + 1 : t;
             AZB_TIMED(1, azt_mbar_wait(&bar_mma_done[last & 7], (last >> 3) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;");
             const long long tb_ = prof_on ? clock64() : 0;
-            const int blk = AZB_RING(j);
+            const int blk = AZB_RING(t);
             const uint32_t ta = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)blk * 64u + (uint32_t)half * 32u;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -649,8 +718,8 @@ k_resblock(const azb_params p)
 #pragma unroll
                 for (int g = 0; g < 2; g++) {
                     const int c8 = half * 4 + h * 2 + g;            // 8-channel chunk of the row
-                    const float4 b0 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8]);
-                    const float4 b1 = *reinterpret_cast<const float4 *>(&s_bias[c8 * 8 + 4]);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&bias[c8 * 8]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&bias[c8 * 8 + 4]);
                     float f[8];
                     f[0] = __uint_as_float(acc[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(acc[g * 8 + 1]) + b0.y;
                     f[2] = __uint_as_float(acc[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(acc[g * 8 + 3]) + b0.w;
@@ -698,7 +767,7 @@ k_resblock(const azb_params p)
         unsigned long long *row = p.prof + ((size_t)rank * 8 + role) * 8;
         for (int k = 0; k < 6; k++) row[k] = (unsigned long long)prof_acc[k];
         row[6] = (unsigned long long)(clock64() - prof_t0);
-        row[7] = (unsigned long long)nslabs;
+        row[7] = (unsigned long long)NT;
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();

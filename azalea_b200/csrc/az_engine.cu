@@ -1188,16 +1188,14 @@ size_t az_nn_resblock_scratch_bytes(void)
     return AZB_VIA_L2 ? (size_t)(az_sm_count(az_current_device()) / 2) * AZB_R * AZT_OUT_BYTES : 0;
 }
 
-int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
-                   int board_size, int64_t num_boards, void *stream)
+static int azb_launch(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
+                      int board_size, int64_t num_boards, int passes, void *stream)
 {
-    if (!x_dev || !w_dev || !bias_dev || (AZB_VIA_L2 && !scratch_dev) || board_size < 2 || board_size > 19 || num_boards < 0)
-        return AZ_E_INVALID;
-    if (num_boards == 0) return AZ_OK;
     azb_params p = {};
     p.x = (uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
+    p.passes = passes;
     p.scratch = (uint8_t *)scratch_dev;
     p.debug = azb_debug;
     p.prof = azb_prof;
@@ -1227,7 +1225,31 @@ int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, void *
     return az_check(cudaGetLastError());
 }
 
-static_assert(AZB_SMEM_BYTES + 2048 <= 232448, "k_resblock: dynamic + static shared memory per CTA");
+int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
+                   int board_size, int64_t num_boards, void *stream)
+{
+    return az_nn_resblocks(x_dev, w_dev, bias_dev, scratch_dev, board_size, num_boards, 1, stream);
+}
+
+int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
+                    int board_size, int64_t num_boards, int num_blocks, void *stream)
+{
+    if (!x_dev || !w_dev || !bias_dev || (AZB_VIA_L2 && !scratch_dev) || board_size < 2 || board_size > 19 ||
+        num_boards < 0 || num_blocks < 0)
+        return AZ_E_INVALID;
+    if (num_boards == 0) return AZ_OK;
+    // the chained form needs the shipped hand-over (one storer thread, staged output)
+    const int chain = (AZB_CDIRECT || AZB_STORERS != 1) ? 1 : AZB_MAXPASS;
+    for (int b = 0; b < num_blocks; b += chain) {
+        const int passes = num_blocks - b < chain ? num_blocks - b : chain;
+        int rc = azb_launch(x_dev, (const uint8_t *)w_dev + (size_t)b * 2 * AZT_WBYTES, bias_dev + (size_t)b * 2 * AZT_C,
+                            scratch_dev, board_size, num_boards, passes, stream);
+        if (rc != AZ_OK) return rc;
+    }
+    return AZ_OK;
+}
+
+static_assert(AZB_SMEM_BYTES + 4096 <= 232448, "k_resblock: dynamic + static shared memory per CTA");
 
 int az_play_commit(az_engine *e, const az_play_params *p, int32_t *chosen_dev, void *stream)
 {

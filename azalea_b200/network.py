@@ -87,9 +87,10 @@ class HexNetwork(nn.Module):
         # 'cudnn': twelve fused cuDNN calls (also used for other widths)
         import os
         self.tower = os.environ.get('AZALEA_B200_TOWER', 'tcgen05')
-        # one fused launch per residual block (csrc/az_block.cuh) instead of
-        # two az_nn_conv3x3 launches; AZALEA_B200_FUSED=0 keeps the two-launch path
-        self.tower_fused = os.environ.get('AZALEA_B200_FUSED', '1') != '0'
+        # the residual tower on the fused kernel (csrc/az_block.cuh): AZALEA_B200_FUSED=2
+        # (default) chains all blocks in one launch, 1 is one launch per block, 0 the
+        # two az_nn_conv3x3 launches per block
+        self.tower_fused = int(os.environ.get('AZALEA_B200_FUSED', '2'))
         nnet = sum(p.nelement() for p in self.parameters())
         nenc = sum(p.nelement() for p in self.encoder.parameters())
         logging.info('Net params: %d  Embedding params: %d', nnet - nenc, nenc)
@@ -196,6 +197,9 @@ class HexNetwork(nn.Module):
             fast['tower_fused'] = [
                 (keep(torch.cat([w1, w2])), keep32(torch.cat([b1, b2])))
                 for (w1, b1), (w2, b2) in fast['tower']]
+            # and all blocks back to back for the chained launch
+            fast['tower_chain'] = (keep(torch.cat([w for w, _ in fast['tower_fused']])),
+                                   keep32(torch.cat([b for _, b in fast['tower_fused']])))
         fast['tower_buf'] = old['tower_buf'] if old is not None else {}
         # the two 1x1 head convolutions read the same activations: one conv;
         # the two first fully connected layers read its output: one GEMM over
@@ -370,8 +374,13 @@ class HexNetwork(nn.Module):
             ev.append((e0, e1, kind, N))
 
         fused = f.get('tower_fused') if self.tower_fused else None
-        if fused is not None:
-            # one launch per residual block (csrc/az_block.cuh), in place
+        if fused is not None and self.tower_fused >= 2:
+            # the whole tower chained in one launch (csrc/az_block.cuh), in place
+            wall, ball = f['tower_chain']
+            timed(lambda: _cabi.check(L.az_nn_resblocks(
+                p(x), p(wall), p(ball), p(scratch), n, npad, len(fused), stream)), 'chain%d' % len(fused))
+        elif fused is not None:
+            # one launch per residual block, in place
             for w12, b12 in fused:
                 timed(lambda: _cabi.check(L.az_nn_resblock(
                     p(x), p(w12), p(b12), p(scratch), n, npad, stream)), 'block')

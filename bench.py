@@ -555,7 +555,9 @@ def run_ours(args):
                                % args.preroll) if args.preroll > 0 else 'opening',
                     'l2_policy': 'working set (node pools, > 1 GB) exceeds the 126 MB L2',
                     'cuda_graph': not args.no_graph, 'streams': n_streams,
-                    'tower': ('fused residual blocks' if getattr(evaluator, 'tower_fused', False)
+                    'tower': (('all residual blocks chained in one launch' if evaluator.tower_fused >= 2
+                               else 'one fused launch per residual block')
+                              if getattr(evaluator, 'tower_fused', 0)
                               and getattr(evaluator, '_fast', {}).get('tower_fused') else 'two launches per block')
                     if args.evaluator == 'net' else None},
             'moves_per_sec': moves_per_sec,
@@ -612,11 +614,16 @@ def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_sr
     n_launch = sum(len(v) for v in kinds.values())
     units = {'plain': 2, 'residual': 3, 'block': 2}
     convs = {'plain': 1, 'residual': 1, 'block': 2}
+    chain = 0
+    for k in kinds:
+        if k.startswith('chain'):       # 'chainK': K residual blocks chained in one launch
+            chain = int(k[5:])
+            units[k], convs[k] = 2 * chain, 2 * chain
     cbytes = sum(nb * cell_bytes * units[k] for k, v in kinds.items() for _, nb in v)
     cflop = sum(nb * conv_flop * convs[k] for k, v in kinds.items() for _, nb in v)
     tflops = cflop / (tot_ms * 1e-3) / 1e12
     gbs = cbytes / (tot_ms * 1e-3) / 1e9
-    fused = 'block' in kinds
+    fused = 'block' in kinds or chain > 0
     out = {
         'kernel': 'k_resblock' if fused else 'k_conv3x3',
         'launches_timed': n_launch, 'avg_launch_ms': tot_ms / n_launch,
@@ -630,13 +637,17 @@ def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_sr
     }
     key = ('k_resblock' if fused else 'k_conv3x3')
     try:
-        out['traffic'] = tj[key][f'{board}x{board}/{boards}']['traffic_bytes']
+        ent = tj[key][f'{board}x{board}/{boards}' + (f'/chain{chain}' if chain else '')]
+        out['traffic'] = ent['traffic_bytes']
     except Exception:
         out['traffic'] = None
+    if chain:
+        out['blocks_per_launch'] = chain
     if fused:
         out.update(bound='tensor', achieved=tflops, peak=bf16_peak, unit='TFLOP/s',
                    frac=tflops / bf16_peak,
-                   note='one launch per residual block: 2 convolutions from one read + one write of '
+                   note=('the residual tower chained in one launch: ' if chain else 'one launch per residual block: ')
+                        + '2 convolutions per block from one read + one write of '
                         'the activations; useful FLOPs exclude the pad cells of the slab layout '
                         '(110 of 128 MMA rows are real cells at 11x11); peak = sustained cuBLAS bf16')
     else:
@@ -877,8 +888,9 @@ def sp_launches(args, per_move, evaluator=None):
         own = 2                 # stem, heads
         if getattr(evaluator, 'tower', None) == 'tcgen05':
             own += 1            # tail
-            fused = getattr(evaluator, 'tower_fused', False) and evaluator._fast.get('tower_fused')
-            own += (1 if fused else 2) * len(evaluator.resblocks)
+            level = int(getattr(evaluator, 'tower_fused', 0)) if evaluator._fast.get('tower_fused') else 0
+            nblk = len(evaluator.resblocks)
+            own += 2 * nblk if level == 0 else nblk if level == 1 else -(-nblk // 8)
         per += (nb + 1) * own
     return per
 

@@ -331,6 +331,18 @@ size_t az_nn_resblock_scratch_bytes(void);
 int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev,
                    void *scratch_dev, int board_size, int64_t num_boards,
                    void *stream);
+/* The residual tower (network.py:73: nn.Sequential of num_blocks Resblocks):
+ * num_blocks blocks applied one after the other, chained inside one launch
+ * (eight per launch at most, then the next launch).  Every cluster owns a
+ * range of board groups and runs block b + 1 over it as soon as it has
+ * finished block b there -- a board's activations depend on no other board --
+ * so the two-CTA pipeline is filled and drained once per launch, not once per
+ * block; only the weights are exchanged in between.  w: [num_blocks][2]
+ * packed layers, bias f32 [num_blocks][2][64].  Bit-identical to num_blocks
+ * az_nn_resblock calls. */
+int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev,
+                    void *scratch_dev, int board_size, int64_t num_boards,
+                    int num_blocks, void *stream);
 /* Diagnostic: how many two-CTA clusters az_nn_resblock sizes its grid for on
  * the current device (cudaOccupancyMaxActiveClusters; 74 on a B200), 0 before
  * the first launch. */

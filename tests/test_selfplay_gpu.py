@@ -519,6 +519,72 @@ def test_fused_resblock_concurrent_streams():
         assert torch.equal(b.view(torch.int16), ref.view(torch.int16))
 
 
+@pytest.mark.parametrize('n,N,K', ((11, 1, 6), (11, 64, 6), (11, 1029, 3), (19, 9, 6), (2, 1, 6), (2, 300, 2),
+                                   (3, 33, 6), (7, 91, 6), (13, 2000, 6), (11, 4100, 10), (11, 40960, 6)))
+def test_chained_tower_equals_block_launches(n, N, K):
+    """az_nn_resblocks chains K residual blocks inside one launch (every
+    cluster runs block b + 1 over its own range of board groups as soon as it
+    has finished block b there; K > 8 continues in a second launch): bit-
+    identical to K az_nn_resblock launches -- network.py:73, the tower is a
+    plain nn.Sequential of Resblocks."""
+    import ctypes
+    from azalea_b200 import _cabi, tower_layout as tl
+    L = _cabi.lib()
+    torch.manual_seed(300 + n + K)
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    wall = torch.cat([tl.pack_conv_weights((torch.randn(64, 64, 3, 3, device='cuda') * 0.05).to(torch.bfloat16))
+                      for _ in range(2 * K)]).contiguous()
+    ball = (torch.randn(2 * K * 64, device='cuda') * 0.1).contiguous()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    scratch = torch.zeros(max(16, L.az_nn_resblock_scratch_bytes()), dtype=torch.uint8, device='cuda')
+    xa, xb = tl.to_slabs(x), tl.to_slabs(x)
+    wbytes = wall.numel() * wall.element_size() // K
+    for b in range(K):
+        _cabi.check(L.az_nn_resblock(p(xa), ctypes.c_void_p(wall.data_ptr() + b * wbytes),
+                                     ctypes.cast(ball.data_ptr() + b * 128 * 4, ctypes.POINTER(ctypes.c_float)),
+                                     p(scratch), n, N, stream))
+    for _ in range(3 if N <= 4100 else 1):      # repeated: the hand-over between passes is a timing matter
+        xb.copy_(tl.to_slabs(x))
+        _cabi.check(L.az_nn_resblocks(p(xb), p(wall), ctypes.cast(ball.data_ptr(), ctypes.POINTER(ctypes.c_float)),
+                                      p(scratch), n, N, K, stream))
+        torch.cuda.synchronize()
+        assert torch.equal(xa.view(torch.int16), xb.view(torch.int16))
+    _, rest = tl.from_slabs(xb, n, N)
+    assert rest == 0.0
+
+
+def test_chained_tower_concurrent_streams():
+    """Two chained towers in flight on two streams (LockstepSelfPlay(streams=2)
+    evaluates its two windows like this), repeatedly, on their own buffers."""
+    import ctypes
+    from azalea_b200 import _cabi, tower_layout as tl
+    L = _cabi.lib()
+    n, N, K = 11, 10240, 6
+    torch.manual_seed(8)
+    x = (torch.randn(N, n, n, 64, device='cuda') * 0.5).to(torch.bfloat16)
+    wall = torch.cat([tl.pack_conv_weights((torch.randn(64, 64, 3, 3, device='cuda') * 0.03).to(torch.bfloat16))
+                      for _ in range(2 * K)]).contiguous()
+    ball = (torch.randn(2 * K * 64, device='cuda') * 0.1).contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    fp = lambda t: ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+    ref = tl.to_slabs(x)
+    reps = 8
+    st0 = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for _ in range(reps):
+        _cabi.check(L.az_nn_resblocks(p(ref), p(wall), fp(ball), None, n, N, K, st0))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    bufs = [tl.to_slabs(x) for _ in streams]
+    torch.cuda.synchronize()
+    for _ in range(reps):
+        for s, b in zip(streams, bufs):
+            _cabi.check(L.az_nn_resblocks(p(b), p(wall), fp(ball), None, n, N, K, ctypes.c_void_p(s.cuda_stream)))
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b.view(torch.int16), ref.view(torch.int16))
+
+
 def test_tcgen05_tower_matches_cudnn_tower():
     """The whole evaluator with the tcgen05 tower (AZALEA_B200_TOWER=tcgen05)
     against the default cuDNN tower on the same weights: both are bf16 with

@@ -1,4 +1,4 @@
-// az_block.cuh -- one residual block of the evaluator's tower in ONE launch (sm_100a):
+// az_block.cuh -- the residual blocks of the evaluator's tower, one or all of them per launch (sm_100a):
 //     x <- relu(conv2(relu(conv1(x) + b1)) + b2 + x)         (network.py:17-39, BN folded)
 // on tcgen05 tensor cores, in place, reading x once and writing it once.
 //
@@ -55,12 +55,26 @@
 // Everything else -- slab layout, pointer-shift taps, dy stacking into a TMEM accumulator
 // ring, ping-pong MMA issuers, two epilogue groups -- is az_tower.cuh's; see there.
 //
+// CHAINED BLOCKS (az_nn_resblocks, `passes` > 1): a board's activations depend on no other
+// board, so a cluster runs block b + 1 over its own range of groups as soon as it has finished
+// block b there -- no grid-wide synchronisation, and the P -> C pipeline is filled and drained
+// once per launch instead of once per block (a launch costs ~14 us beyond its slabs; +4.7 %
+// simulations/s in the step).  The slab index t = pass * nslabs + j simply runs on: rings,
+// barrier phases and the TMEM ring continue across a pass boundary (nslabs is a multiple of the
+// board size, so the board row is t % n), j addresses memory.  Added for it: all passes' biases
+// in shared memory; a "weights" thread per CTA that follows every slab's MMA-retired barrier
+// (a parity wait is only sound one phase away) and loads the next pass's weights when the last
+// slab of a pass has retired; and s_stored, the count of output slabs whose bulk store has
+// COMPLETED, kept by C's storer in both CTAs' shared memory -- P's loader (its next input) and
+// C's residual loader wait for it before they read a slab again.
+//
 // Roles (672 threads per CTA):
 //   warps 0-15   epilogue (two groups of eight on alternate output slabs)
 //   warps 16,17  MMA issuers (even / odd slabs)
-//   warp 18      loader: weights; P: x chunks (144 rows); C: residual slabs (128 rows)
-//   warp 19      C: relay (slab landed -> P.out_empty; MMA2 retired -> re-arm, P.y_free)
-//   warp 20      storer: P: staging tile -> C's ring; C: staging tile -> x
+//   warp 18      loader: P: x chunks (144 rows); C: residual slabs (128 rows)
+//   warp 19      lane 0, C: relay (slab landed -> P.out_empty; MMA2 retired -> re-arm, P.y_free)
+//                lane 1, both: this CTA's weights, pass after pass
+//   warp 20      storer: P: staging tile -> C's ring; C: staging tile -> x, and s_stored
 #pragma once
 
 #include "az_tower.cuh"

@@ -165,8 +165,15 @@ __global__ void k_noise_sample(az_engine e, float alpha, int k, int sim, float *
 
 // ------------------------------------------------------------------ select
 
+// Register budget of k_select<4>: 7 CTAs of four warps per SM = 72 registers.  4096 games are 27.7
+// warps per SM, so 7 CTAs still hold them all in one wave; measured tree-only throughput by
+// minimum CTAs per SM (registers): 8 (64) 1.685e8, 7 (72) 1.746e8, 6 (80) 1.53e8, 5 (96) 1.59e8,
+// 4 (120, the first setting without spills) 1.69e8 simulations/s.
+#ifndef AZ_SELECT_MINBLOCKS
+#define AZ_SELECT_MINBLOCKS 7
+#endif
 template <int MAXS, bool NOISE>
-__global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32, MAXS <= 4 ? 8 : 3)
+__global__ void __launch_bounds__(AZ_WARPS_PER_CTA * 32, MAXS <= 4 ? AZ_SELECT_MINBLOCKS : 3)
 k_select(az_engine e, az_select_args a)
 {
     __shared__ uint32_t smask_all[AZ_WARPS_PER_CTA][64];

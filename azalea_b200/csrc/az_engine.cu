@@ -1239,7 +1239,7 @@ int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev, void 
         return AZ_E_INVALID;
     if (num_boards == 0) return AZ_OK;
     // the chained form needs the shipped hand-over (one storer thread, staged output)
-    const int chain = (AZB_CDIRECT || AZB_STORERS != 1) ? 1 : AZB_MAXPASS;
+    const int chain = (AZB_CDIRECT || AZB_STORERS != 1 || AZB_HANDOVER != 0) ? 1 : AZB_MAXPASS;
     for (int b = 0; b < num_blocks; b += chain) {
         const int passes = num_blocks - b < chain ? num_blocks - b : chain;
         int rc = azb_launch(x_dev, (const uint8_t *)w_dev + (size_t)b * 2 * AZT_WBYTES, bias_dev + (size_t)b * 2 * AZT_C,

@@ -17,10 +17,11 @@ AZ_OK = 0
 AZ_ST_POOL_FULL, AZ_ST_TREE_FULL, AZ_ST_ILLEGAL, AZ_ST_DISABLED = 1, 2, 4, 8
 AZ_LEAF_TERMINAL_KNOWN, AZ_LEAF_TERMINAL_NEW = 1, 2
 AZ_PRIOR_PROBS, AZ_PRIOR_LOGITS = 0, 1
-AZ_CFG_SOFT_POOL_FULL = 1
-AZ_ABI_VERSION = 2
+AZ_CFG_SOFT_POOL_FULL, AZ_CFG_PACK_LEAVES = 1, 2
+AZ_ABI_VERSION = 3
 (AZ_BUF_LEAF_BOARD, AZ_BUF_LEAF_INFO, AZ_BUF_VALUE, AZ_BUF_PRIOR, AZ_BUF_META,
- AZ_BUF_REPLAY, AZ_BUF_COUNTERS, AZ_BUF_LEAF_MOVES, AZ_BUF_GLOBALS) = range(9)
+ AZ_BUF_REPLAY, AZ_BUF_COUNTERS, AZ_BUF_LEAF_MOVES, AZ_BUF_GLOBALS,
+ AZ_BUF_LEAF_ROWS) = range(10)
 COUNTER_NAMES = ('simulations', 'sum_children', 'sum_depth', 'unique_leaves',
                  'expanded_children', 'plies', 'games', 'replay_rows',
                  'replay_dropped', 'games_failed', 'compacted_nodes',
@@ -112,6 +113,9 @@ def lib():
     L.az_nn_heads.argtypes = [vp, C.c_int64, f32p, f32p, vp, C.c_int64, C.c_int, C.c_int, C.c_int, vp]
     L.az_nn_tail.argtypes = [vp, C.c_int64, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p,
                              f32p, C.c_int64, f32p, C.c_int64, vp]
+    L.az_nn_stem_live.argtypes = L.az_nn_stem.argtypes[:-1] + [i32p, vp]
+    L.az_nn_heads_live.argtypes = L.az_nn_heads.argtypes[:-1] + [i32p, vp]
+    L.az_nn_tail_live.argtypes = L.az_nn_tail.argtypes[:-1] + [i32p, vp]
     L.az_nn_tower_group.argtypes = [C.c_int]
     L.az_nn_tower_halo.argtypes = [C.c_int]
     L.az_nn_tower_rows.argtypes = [C.c_int, C.c_int64]
@@ -119,6 +123,7 @@ def lib():
     L.az_nn_conv3x3.argtypes = [vp, vp, f32p, vp, vp, C.c_int, C.c_int64, vp]
     L.az_nn_resblock.argtypes = [vp, vp, f32p, vp, C.c_int, C.c_int64, vp]
     L.az_nn_resblocks.argtypes = [vp, vp, f32p, vp, C.c_int, C.c_int64, C.c_int, vp]
+    L.az_nn_resblocks_live.argtypes = L.az_nn_resblocks.argtypes[:-1] + [i32p, vp]
     L.az_nn_resblock_scratch_bytes.restype = C.c_size_t
     L.az_noise_sample.argtypes = [eng, C.c_float, C.c_int, C.c_int, f32p, vp]
     L.az_play_commit.argtypes = [eng, C.POINTER(AzPlayParams), i32p, vp]

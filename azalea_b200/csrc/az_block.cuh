@@ -155,6 +155,7 @@ struct azb_params {
     int passes;             // residual blocks to apply, one after the other (1 .. AZB_MAXPASS)
     uint8_t *scratch;       // AZB_VIA_L2: [clusters][AZB_R][16 KB] hand-over ring in global memory
     unsigned long long *prof;   // probe only: per-role wait cycles of cluster 0 ([rank][32]) or NULL
+    const int *live;        // packed leaves: device count of boards that are live in this batch (or NULL: all)
     int debug;              // probe only (tools/probe/block_time.py): 2 = C skips its global stores,
                             // 4 = C skips the residual loads, 8 = no MMAs
 };
@@ -289,7 +290,7 @@ struct azb_pos {
     __device__ __forceinline__ void advance(int step, int nslabs)
     {
         t += step; j += step;
-        while (j >= nslabs) { j -= nslabs; pass++; }
+        while (nslabs > 0 && j >= nslabs) { j -= nslabs; pass++; }
     }
 };
 
@@ -319,6 +320,14 @@ k_resblock(const azb_params p)
     const bool prof_on = AZB_PROF && p.prof != nullptr && (blockIdx.x >> 1) == 0 && lane == 0;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = clock64();
+    // probe (debug & 16, tools/probe/cluster_times.py): when each CTA started and ended, and where
+    if ((p.debug & 16) && p.prof != nullptr && tid == 0) {
+        unsigned long long gt; uint32_t smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        p.prof[128 + 4 * blockIdx.x] = gt;
+        p.prof[128 + 4 * blockIdx.x + 2] = smid;
+    }
     if (tid == 0) {
         azt_mbar_init(&bar_w, 1);
         for (int i = 0; i < AZB_SMAX; i++) azt_mbar_init(&bar_in_full[i], 1);   // one bulk transfer per stage
@@ -362,7 +371,14 @@ k_resblock(const azb_params p)
     // in all, t = pass * nslabs + j; board row y = t % n
     const int n = p.n;
     const long long cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
-    const long long g0 = p.groups * cid / ncl, g1 = p.groups * (cid + 1) / ncl;
+    // packed leaves: the batch holds *live boards, known only on the device; the grid was sized
+    // for p.groups, clusters left without a group fall through every role
+    long long groups = p.groups;
+    if (p.live != nullptr) {
+        const long long lg = ((long long)*p.live + p.bpg - 1) / p.bpg;
+        groups = lg < groups ? lg : groups;
+    }
+    const long long g0 = groups * cid / ncl, g1 = groups * (cid + 1) / ncl;
     const long long q0 = g0 * n;
     const int nslabs = (int)((g1 - g0) * n);
     const int NT = nslabs * p.passes;
@@ -380,7 +396,10 @@ k_resblock(const azb_params p)
     // both CTAs' barriers are initialised (and C's ring zeroed) before either touches the other's
     azb_cluster_sync();
 
-    if (warp >= 20) {
+    if (NT == 0) {
+        // packed leaves: fewer live groups than clusters -- this one has nothing to do (both of its
+        // CTAs agree); it still takes part in the two cluster barriers and frees its TMEM
+    } else if (warp >= 20) {
         // ----------------------------------------------------------- storers --
         // A bulk store takes ~1000 cycles to read its 16 KB tile, and bulk groups are per
         // thread: one storer thread that waits for each store's read before it hands the tile
@@ -450,7 +469,7 @@ k_resblock(const azb_params p)
             // "MMA retired" barrier in order (a parity wait is only sound one phase away), and
             // loads the next pass's weights when the last slab of a pass has retired.
             const uint8_t *w = p.w + (size_t)rank * AZT_WBYTES;
-            for (int pass = 0; pass < p.passes; pass++) {
+            for (int pass = 0; pass < p.passes && NT > 0; pass++) {
                 if (pass > 0)
                     for (int t = (pass - 1) * nslabs; t < pass * nslabs; t++)
                         azt_mbar_wait(&bar_mma_done[t & 7], (t >> 3) & 1);
@@ -785,6 +804,12 @@ k_resblock(const azb_params p)
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
+    if ((p.debug & 16) && p.prof != nullptr && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        p.prof[128 + 4 * blockIdx.x + 1] = gt;
+        p.prof[128 + 4 * blockIdx.x + 3] = (unsigned long long)NT;
+    }
     // neither CTA may leave while the other can still reach into its shared memory
     azb_cluster_sync();
     if (warp == 0)

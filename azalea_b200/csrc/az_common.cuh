@@ -63,6 +63,7 @@ struct az_engine {
     float *prior;           // [G][B][nn]
     unsigned long long *counters;   // [G][16]
     unsigned long long *globals;    // [16] (replay append cursor etc.)
+    int32_t *leaf_rows;     // [G]: [g0] = live packed leaf rows of the window starting at g0
     uint8_t *hist;          // [G][hist_rows][row_bytes]
     uint8_t *replay;        // [replay_rows][row_bytes]
     az_buffer_desc desc[AZ_BUF__COUNT];

@@ -725,6 +725,7 @@ static int az_layout(az_engine *e, const az_config *cfg)
     size_t o_prior = off; off = az_align(off + (size_t)e->G * e->B * e->nn * 4);
     size_t o_cnt = off; off = az_align(off + (size_t)e->G * AZ_CNT_PER_GAME * 8);
     size_t o_glob = off; off = az_align(off + 16 * 8);
+    size_t o_lrows = off; off = az_align(off + (size_t)e->G * 4);
     size_t o_hist = off; off = az_align(off + (size_t)e->G * e->hist_rows * e->row_bytes);
     size_t o_replay = off; off = az_align(off + (size_t)e->cfg.replay_rows * e->row_bytes);
     e->total_bytes = off;
@@ -741,6 +742,7 @@ static int az_layout(az_engine *e, const az_config *cfg)
     e->prior = (float *)o_prior;
     e->counters = (unsigned long long *)o_cnt;
     e->globals = (unsigned long long *)o_glob;
+    e->leaf_rows = (int32_t *)o_lrows;
     e->hist = (uint8_t *)o_hist;
     e->replay = (uint8_t *)o_replay;
 #define AZ_DESC(which, off_, bytes_, elem_, nd_, s0, s1, s2, s3)                         \
@@ -758,6 +760,7 @@ static int az_layout(az_engine *e, const az_config *cfg)
     AZ_DESC(AZ_BUF_COUNTERS, o_cnt, (size_t)e->G * AZ_CNT_PER_GAME * 8, 8, 2, e->G, AZ_CNT_PER_GAME, 0, 0);
     AZ_DESC(AZ_BUF_LEAF_MOVES, o_lmoves, (size_t)e->G * e->B * e->nn * 4, 4, 3, e->G, e->B, e->nn, 0);
     AZ_DESC(AZ_BUF_GLOBALS, o_glob, 16 * 8, 8, 1, 16, 0, 0, 0);
+    AZ_DESC(AZ_BUF_LEAF_ROWS, o_lrows, (size_t)e->G * 4, 4, 1, e->G, 0, 0, 0);
 #undef AZ_DESC
     return AZ_OK;
 }
@@ -815,6 +818,7 @@ int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_
     AZ_BIND(prior, float *);
     AZ_BIND(counters, unsigned long long *);
     AZ_BIND(globals, unsigned long long *);
+    AZ_BIND(leaf_rows, int32_t *);
     AZ_BIND(hist, uint8_t *);
     AZ_BIND(replay, uint8_t *);
 #undef AZ_BIND
@@ -823,6 +827,7 @@ int az_engine_create(az_engine **out, const az_config *cfg, void *mem_dev, size_
     // no leaves yet: node = -1 in every slot
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->leaf_info, 0xff, (size_t)e->G * e->B * sizeof(int4), 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->meta, 0, (size_t)e->G * AZ_META_INTS * 4, 0));
+    if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->leaf_rows, 0, (size_t)e->G * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->value, 0, (size_t)e->G * e->B * 4, 0));
     if (rc == AZ_OK) rc = az_check(cudaMemsetAsync(e->prior, 0, (size_t)e->G * e->B * e->nn * 4, 0));
     // replay rows carry alignment padding that no kernel writes
@@ -1020,6 +1025,15 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
                const void *table_dev, const float *bias_dev, void *out_dev, int channels,
                int padded_layout, void *stream)
 {
+    return az_nn_stem_live(cells_dev, cell_stride, board_size, num_boards, table_dev, bias_dev, out_dev,
+                           channels, padded_layout, nullptr, stream);
+}
+
+int az_nn_stem_live(const int8_t *cells_dev, int cell_stride, int board_size, int64_t num_boards,
+                    const void *table_dev, const float *bias_dev, void *out_dev, int channels,
+                    int padded_layout, const int32_t *live_rows_dev, void *stream)
+{
+    if (live_rows_dev && !padded_layout) return AZ_E_UNSUPPORTED;
     if (padded_layout && channels != 64) return AZ_E_UNSUPPORTED;
     if (!cells_dev || !table_dev || !bias_dev || !out_dev || board_size < 2 || board_size > 19 ||
         channels < 8 || channels > AZ_NN_MAXC || (channels & 7) || num_boards < 0 ||
@@ -1041,7 +1055,7 @@ int az_nn_stem(const int8_t *cells_dev, int cell_stride, int board_size, int64_t
         if (blocks > az_sm_count(dev) * 6) blocks = az_sm_count(dev) * 6;
         k_nn_stem_slab<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
             cells_dev, cell_stride, board_size, (long long)num_boards, (const uint16_t *)table_dev,
-            bias_dev, (uint16_t *)out_dev);
+            bias_dev, (uint16_t *)out_dev, live_rows_dev);
         return az_check(cudaGetLastError());
     }
     const int pnn = (board_size + 2) * (board_size + 2);
@@ -1061,6 +1075,15 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
                 void *out_dev, int64_t out_board_stride, int channels, int heads, int padded_board_size,
                 void *stream)
 {
+    return az_nn_heads_live(x_dev, positions, w_dev, b_dev, out_dev, out_board_stride, channels, heads,
+                            padded_board_size, nullptr, stream);
+}
+
+int az_nn_heads_live(const void *x_dev, int64_t positions, const float *w_dev, const float *b_dev,
+                     void *out_dev, int64_t out_board_stride, int channels, int heads, int padded_board_size,
+                     const int32_t *live_rows_dev, void *stream)
+{
+    if (live_rows_dev && !padded_board_size) return AZ_E_UNSUPPORTED;
     if (out_board_stride && !padded_board_size) return AZ_E_UNSUPPORTED;
     if (padded_board_size && channels != 64) return AZ_E_UNSUPPORTED;
     if (!x_dev || !w_dev || !b_dev || !out_dev || channels < 8 || channels > AZ_NN_MAXC ||
@@ -1079,7 +1102,8 @@ int az_nn_heads(const void *x_dev, int64_t positions, const float *w_dev, const 
         long long blocks = (boards + bpg - 1) / bpg * n;
         if (blocks > 148 * 8) blocks = 148 * 8;
         k_nn_heads_slab<6><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-            (const uint16_t *)x_dev, boards, n, w_dev, b_dev, (uint16_t *)out_dev, (long long)out_board_stride);
+            (const uint16_t *)x_dev, boards, n, w_dev, b_dev, (uint16_t *)out_dev, (long long)out_board_stride,
+            live_rows_dev);
         return az_check(cudaGetLastError());
     }
     long long blocks = (positions * (channels >> 3) + 255) / 256;
@@ -1095,6 +1119,15 @@ int az_nn_tail(const void *y_dev, int64_t num_boards, int ld, int nfc2, int boar
                float *value_dev, int64_t value_stride, float *logits_dev, int64_t logits_stride,
                void *stream)
 {
+    return az_nn_tail_live(y_dev, num_boards, ld, nfc2, board_size, fc_bias_dev, w3_dev, b3_dev, value_dev,
+                           value_stride, logits_dev, logits_stride, nullptr, stream);
+}
+
+int az_nn_tail_live(const void *y_dev, int64_t num_boards, int ld, int nfc2, int board_size,
+                    const float *fc_bias_dev, const float *w3_dev, const float *b3_dev,
+                    float *value_dev, int64_t value_stride, float *logits_dev, int64_t logits_stride,
+                    const int32_t *live_rows_dev, void *stream)
+{
     const int nn = board_size * board_size;
     if (!y_dev || !fc_bias_dev || !w3_dev || !b3_dev || board_size < 2 || board_size > 19 ||
         num_boards < 0 || nfc2 < 2 || (nfc2 & 1) || ld < nfc2 + nn || (ld & 1) ||
@@ -1106,7 +1139,7 @@ int az_nn_tail(const void *y_dev, int64_t num_boards, int ld, int nfc2, int boar
     if (blocks > cap) blocks = cap;
     k_nn_tail<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         (const uint16_t *)y_dev, (long long)num_boards, ld, nfc2, nn, fc_bias_dev, w3_dev, b3_dev,
-        value_dev, (long long)value_stride, logits_dev, (long long)logits_stride);
+        value_dev, (long long)value_stride, logits_dev, (long long)logits_stride, live_rows_dev);
     return az_check(cudaGetLastError());
 }
 
@@ -1189,9 +1222,10 @@ size_t az_nn_resblock_scratch_bytes(void)
 }
 
 static int azb_launch(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
-                      int board_size, int64_t num_boards, int passes, void *stream)
+                      int board_size, int64_t num_boards, int passes, const int32_t *live_rows_dev, void *stream)
 {
     azb_params p = {};
+    p.live = live_rows_dev;
     p.x = (uint8_t *)x_dev; p.w = (const uint8_t *)w_dev; p.bias = bias_dev;
     p.n = board_size; p.bpg = 128 / (board_size + 1);
     p.groups = (num_boards + p.bpg - 1) / p.bpg;
@@ -1234,6 +1268,14 @@ int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev, void *
 int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
                     int board_size, int64_t num_boards, int num_blocks, void *stream)
 {
+    return az_nn_resblocks_live(x_dev, w_dev, bias_dev, scratch_dev, board_size, num_boards, num_blocks,
+                                nullptr, stream);
+}
+
+int az_nn_resblocks_live(void *x_dev, const void *w_dev, const float *bias_dev, void *scratch_dev,
+                         int board_size, int64_t num_boards, int num_blocks, const int32_t *live_rows_dev,
+                         void *stream)
+{
     if (!x_dev || !w_dev || !bias_dev || (AZB_VIA_L2 && !scratch_dev) || board_size < 2 || board_size > 19 ||
         num_boards < 0 || num_blocks < 0)
         return AZ_E_INVALID;
@@ -1243,7 +1285,7 @@ int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev, void 
     for (int b = 0; b < num_blocks; b += chain) {
         const int passes = num_blocks - b < chain ? num_blocks - b : chain;
         int rc = azb_launch(x_dev, (const uint8_t *)w_dev + (size_t)b * 2 * AZT_WBYTES, bias_dev + (size_t)b * 2 * AZT_C,
-                            scratch_dev, board_size, num_boards, passes, stream);
+                            scratch_dev, board_size, num_boards, passes, live_rows_dev, stream);
         if (rc != AZ_OK) return rc;
     }
     return AZ_OK;

@@ -89,57 +89,103 @@ __device__ __forceinline__ void az_emit_board(const az_engine &e, uint32_t *smas
 // rng.dirichlet(np.full(k, alpha)); statistical parity, not bit parity).
 // eta = g / sum(g) with g ~ Gamma(alpha) by Ahrens-Dieter GS (exact for
 // alpha <= 1; larger alpha adds floor(alpha) exponentials), kept in logs
-// because alpha = 0.03 puts most samples far below FLT_MIN before
-// normalisation.  Counter-based: (simulation, child, ply) -> Philox4x32-7.
+// (base 2: one MUFU per log / exp) because alpha = 0.03 puts most samples far
+// below FLT_MIN before normalisation.  Counter-based: (simulation, child, ply)
+// -> Philox4x32-7; one block serves the first attempt of the two children
+// lane + 32 s and lane + 32 (s + 1) (x, y | z, w), straight-line.  GS rejects
+// 3.4 % of its candidates at alpha = 0.03, i.e. about four of a warp's 121
+// children per simulation: the rejected ones go round a small loop whose
+// uniforms come from a counter hash of (key, simulation, child, ply, attempt)
+// -- a full Philox block per retry was most of the generator's cost.
+__device__ __forceinline__ float az_lg2(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float az_ex2(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float az_u01f(uint32_t r)    // (0,1), one FMA
+{
+    return __fmaf_rn((float)(r >> 8), 1.0f / 16777216.0f, 0.5f / 16777216.0f);
+}
+
+// One GS attempt for Gamma(a), a <= 1, from two uniforms: r2 = log2 of the candidate; accepted?
+__device__ __forceinline__ bool az_gs_try(uint32_t b1, uint32_t b2, float bgs, float agx,
+                                          float inv_alpha, float &r2)
+{
+    const float pgs = bgs * az_u01f(b1);
+    const float l2 = az_lg2(az_u01f(b2));
+    if (pgs <= 1.0f) {
+        r2 = az_lg2(pgs) * inv_alpha;                   // X = P^(1/alpha)
+        return l2 <= -1.44269504f * az_ex2(r2);         // U2 <= exp(-X)
+    }
+    r2 = az_lg2(-0.69314718f * az_lg2((bgs - pgs) * inv_alpha));    // X = -ln((b - P) / alpha)
+    return l2 <= (agx - 1.0f) * r2;                     // U2 <= X^(alpha-1)
+}
+
 template <int MAXS>
-__device__ __forceinline__ void az_dirichlet_noise(int k, float alpha, uint32_t sim,
+__device__ __forceinline__ void az_dirichlet_noise(int lane, int k, float alpha, uint32_t sim,
                                                    uint32_t ply, uint2 key, float (&noise)[MAXS])
 {
-    const int lane = az_lane();
+    static_assert(MAXS % 2 == 0, "children are drawn in pairs");
     const float alpha_frac = alpha > 1.0f ? alpha - floorf(alpha) : alpha;
     const float agx = alpha_frac > 0.0f ? alpha_frac : 1.0f;
     const float inv_alpha = 1.0f / agx;
     const float bgs = (2.7182818f + agx) / 2.7182818f;
-    float lg[MAXS], mx = -INFINITY;
+    float lg[MAXS];
+    uint32_t todo = 0;                                  // bit s: child lane + 32 s still has no sample
 #pragma unroll
-    for (int s = 0; s < MAXS; s++) {
-        const int j = lane + 32 * s;
-        float r = -INFINITY;
-        if (j < k) {
-            for (uint32_t att = 0; att < 8u; att++) {
-                const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j, ply, 0xD1C10000u + att), key);
-                bool ok = false;
-#pragma unroll
-                for (int h = 0; h < 2 && !ok; h++) {
-                    const float pgs = bgs * az_u01(h ? u.z : u.x);
-                    const float lu2 = __logf(az_u01(h ? u.w : u.y));
-                    if (pgs <= 1.0f) {
-                        r = __logf(pgs) * inv_alpha;        // ln X, X = P^(1/alpha)
-                        ok = lu2 <= -__expf(r);             // U2 <= exp(-X)
-                    } else {
-                        const float xg = -__logf((bgs - pgs) * inv_alpha);
-                        r = __logf(xg);
-                        ok = lu2 <= (agx - 1.0f) * r;       // U2 <= X^(alpha-1)
-                    }
-                }
-                if (ok) break;
-            }
-            if (alpha > 1.0f) {
-                float tot = (alpha_frac > 0.0f) ? __expf(r) : 0.0f;
-                for (int m = 0; m < (int)alpha; m++) {
-                    const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j, ply, 0xE9000000u + m), key);
-                    tot -= __logf(az_u01(u.x));
-                }
-                r = __logf(tot);
-            }
-            mx = fmaxf(mx, r);
+    for (int s = 0; s < MAXS; s += 2) {
+        lg[s] = lg[s + 1] = -INFINITY;
+        if (32 * s < k) {                               // warp-uniform
+            const int j0 = lane + 32 * s;
+            const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j0, ply, 0xD1C10000u), key);
+            float c;
+            if (j0 < k) { if (az_gs_try(u.x, u.y, bgs, agx, inv_alpha, c)) lg[s] = c; else todo |= 1u << s; }
+            if (j0 + 32 < k) { if (az_gs_try(u.z, u.w, bgs, agx, inv_alpha, c)) lg[s + 1] = c; else todo |= 2u << s; }
         }
-        lg[s] = r;
     }
-    for (int off = 16; off; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(AZ_FULL, mx, off));
+    if (__any_sync(AZ_FULL, todo != 0u)) {
+        const uint32_t h0 = key.x ^ (sim * 0x9E3779B9u) ^ (ply * 0xC2B2AE35u) ^ ((uint32_t)lane * 0x85EBCA6Bu);
+#pragma unroll 1
+        for (uint32_t att = 1; att < 24u && todo != 0u; att++) {
+#pragma unroll
+            for (int s = 0; s < MAXS; s++) {
+                if (!((todo >> s) & 1u)) continue;
+                const uint32_t w1 = az_fmix32(h0 + att * 0x27D4EB2Fu + (uint32_t)s * 0x165667B1u);
+                const uint32_t w2 = az_fmix32(w1 ^ key.y);
+                float c;
+                if (az_gs_try(w1, w2, bgs, agx, inv_alpha, c)) { lg[s] = c; todo &= ~(1u << s); }
+            }
+        }
+    }
+    if (alpha > 1.0f) {
+#pragma unroll
+        for (int s = 0; s < MAXS; s++) {
+            const int j = lane + 32 * s;
+            if (j >= k) continue;
+            float tot = (alpha_frac > 0.0f) ? az_ex2(lg[s]) : 0.0f;
+            for (int m = 0; m < (int)alpha; m++) {
+                const uint4 u = az_philox7(make_uint4(sim, (uint32_t)j, ply, 0xE9000000u + m), key);
+                tot -= 0.69314718f * az_lg2(az_u01f(u.x));
+            }
+            lg[s] = az_lg2(tot);
+        }
+    }
+    float mx = lg[0];
+#pragma unroll
+    for (int s = 1; s < MAXS; s++) mx = fmaxf(mx, lg[s]);
+    asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx) : "f"(mx));
     float z = 0.0f;
 #pragma unroll
-    for (int s = 0; s < MAXS; s++) { lg[s] = __expf(lg[s] - mx); z += lg[s]; }
+    for (int s = 0; s < MAXS; s++) { lg[s] = az_ex2(lg[s] - mx); z += lg[s]; }
     for (int off = 16; off; off >>= 1) z += __shfl_xor_sync(AZ_FULL, z, off);
     const float invz = 1.0f / z;
 #pragma unroll
@@ -157,7 +203,7 @@ __global__ void k_noise_sample(az_engine e, float alpha, int k, int sim, float *
     const uint2 key = make_uint2((uint32_t)e.cfg.seed ^ (uint32_t)meta[M_GID_LO],
                                  (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
     float noise[12];
-    az_dirichlet_noise<12>(k, alpha, (uint32_t)sim, (uint32_t)meta[M_PLY], key, noise);
+    az_dirichlet_noise<12>(lane, k, alpha, (uint32_t)sim, (uint32_t)meta[M_PLY], key, noise);
 #pragma unroll
     for (int s = 0; s < 12; s++)
         if (lane + 32 * s < k) out[(size_t)g * k + lane + 32 * s] = noise[s];
@@ -234,8 +280,9 @@ k_select(az_engine e, az_select_args a)
                                  (uint32_t)(e.cfg.seed >> 32) ^ (uint32_t)meta[M_GID_HI]);
     const int sim0 = meta[M_SIM];
     const int ply = meta[M_PLY];
-    int my_leaf = -1, my_depth = 0;         // lane b remembers descent b
-    unsigned long long sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0, term = 0;
+    int my_leaf = -1, my_depth = 0;         // lane b remembers descent b: depth | needs the network << 16 | flip << 17
+    const bool pack = (e.cfg.flags & AZ_CFG_PACK_LEAVES) != 0;
+    uint32_t sum_k = 0, sum_d = 0, uniq = 0, nn_rows = 0, term = 0;   // per launch: small
     const int k0 = (int)(rootlink & AZ_LINK_KMASK), fc0 = (int)(rootlink >> AZ_LINK_KBITS);
     uint32_t touched = 0;                   // bit s: this lane's root child lane + 32 s took a virtual loss
     if (AZ_STAGE_ROOT) {
@@ -267,7 +314,11 @@ k_select(az_engine e, az_select_args a)
             const int sum_n = __reduce_add_sync(AZ_FULL, ni);
             const float sq = __fsqrt_rn((float)sum_n);
             const bool sq_zero = sum_n == 0;
+            // (drawn after the record loads have been issued: the generator hides their latency)
             float noise[MAXS];
+            if (NOISE && depth == 0)
+                az_dirichlet_noise<MAXS>(lane, k, (float)a.noise_alpha, (uint32_t)(sim0 + b),
+                                         (uint32_t)ply, key, noise);
             uint32_t bestkey = 0;
             int bestj = 0x7fffffff;
             // sum N == 0 (first descent into a freshly expanded node): every
@@ -276,9 +327,6 @@ k_select(az_engine e, az_select_args a)
             if (sq_zero) {
                 bestj = lane == 0 ? 0 : 0x7fffffff;
             } else {
-            if (NOISE && depth == 0)
-                az_dirichlet_noise<MAXS>(k, (float)a.noise_alpha, (uint32_t)(sim0 + b),
-                                         (uint32_t)ply, key, noise);
 #pragma unroll
             for (int s = 0; s < MAXS; s++) {
                 const int j = lane + 32 * s;
@@ -351,7 +399,7 @@ k_select(az_engine e, az_select_args a)
         sum_d += depth;
         // deduplicate_leaves: first occurrence wins (mcts.py:139-152)
         const bool dup = __any_sync(AZ_FULL, lane < b && my_leaf == node);
-        if (lane == b) { my_leaf = node; my_depth = depth; }
+        if (lane == b) { my_leaf = node; my_depth = depth; }    // (bits 16, 17 are set below)
         if (dup) {
             if (lane == 0) info[b] = make_int4(-1, 0, 0, depth);
             continue;
@@ -368,7 +416,9 @@ k_select(az_engine e, az_select_args a)
                 term++;
             } else {
                 kk = az_count_bits(~(x | o) & valid);
-                az_emit_board(e, smask, x, o, color == 2, lboard + (size_t)b * e.cell_stride);
+                // packed leaves: the board is written once the batch's rows have been reserved
+                if (!pack) az_emit_board(e, smask, x, o, color == 2, lboard + (size_t)b * e.cell_stride);
+                else if (lane == b) my_depth |= (1 << 16) | ((color == 2) << 17);
                 nn_rows++;
             }
             if (lane < e.NW) {
@@ -379,6 +429,27 @@ k_select(az_engine e, az_select_args a)
         if (lane == 0) info[b] = make_int4(node, flags | ((color - 1) << 8), kk, depth);
     }
     __syncwarp();
+    if (pack) {
+        // AZ_CFG_PACK_LEAVES: the leaves the network must evaluate (unique, not terminal:
+        // mcts.py:75,192-200) of all games of the window go to consecutive rows -- one
+        // reservation per game and batch, then the boards from the masks kept per leaf
+        const uint32_t nnmask = __ballot_sync(AZ_FULL, (my_depth >> 16) & 1);
+        int row = 0;
+        if (lane == 0 && nnmask) row = atomicAdd(&e.leaf_rows[e.g0], __popc(nnmask));
+        row = __shfl_sync(AZ_FULL, row, 0);
+        const int cap = (e.g1 - e.g0) * e.B;        // rows of the window (a batch cannot exceed it)
+        for (uint32_t m = nnmask; m; m &= m - 1, row++) {
+            const int b = __ffs(m) - 1;
+            const int meta_b = __shfl_sync(AZ_FULL, my_depth, b);
+            const int r = row < cap ? row : cap - 1;
+            const uint32_t lx = lane < e.NW ? lmask[(size_t)b * 2 * e.NW + lane] : 0u;
+            const uint32_t lo = lane < e.NW ? lmask[(size_t)b * 2 * e.NW + e.NW + lane] : 0u;
+            az_emit_board(e, smask, lx, lo, (meta_b >> 17) & 1,
+                          e.leaf_board + ((size_t)e.g0 * e.B + r) * e.cell_stride);
+            if (lane == 0) info[b].w = (meta_b & 0xffff) | (r << 10);
+        }
+        my_depth &= 0xffff;
+    }
     // undo the virtual losses, leaf list order (mcts.py:72)
     for (int b = 0; b < a.batch; b++) {
         const int depth = __shfl_sync(AZ_FULL, my_depth, b);
@@ -425,6 +496,10 @@ k_expand_backup(az_engine e, az_expand_args a)
     const int lane = az_lane();
     const int g = e.g0 + blockIdx.x * AZ_WARPS_PER_CTA + (threadIdx.x >> 5);
     if (g >= e.g1) return;
+    // packed leaves: the evaluator has consumed this window's batch; the next az_mcts_select
+    // starts a new one
+    const bool pack = (e.cfg.flags & AZ_CFG_PACK_LEAVES) != 0 && !a.root_mode;
+    if (pack && g == e.g0 && lane == 0) e.leaf_rows[e.g0] = 0;
     int32_t *meta = e.meta + (size_t)g * AZ_META_INTS;
     int status = meta[M_STATUS];
     if (status != 0) return;
@@ -442,8 +517,8 @@ k_expand_backup(az_engine e, az_expand_args a)
         const int4 inf = info[b];
         if (inf.x < 0) continue;
         const int node = inf.x, flags = inf.y & 0xff, lcolor = (inf.y >> 8) & 1;
-        const int k = inf.z, depth = inf.w;
-        const size_t row = (size_t)g * e.B + b;
+        const int k = inf.z, depth = pack ? (inf.w & 1023) : inf.w;
+        const size_t row = pack ? (size_t)e.g0 * e.B + (size_t)(inf.w >> 10) : (size_t)g * e.B + b;
         // evaluate_batch, mcts.py:192-200: terminal positions are worth -1
         // to the player to move
         const float v = flags ? -1.0f : a.value[row];

@@ -38,6 +38,8 @@ __device__ __forceinline__ uint32_t az_pack_bf16x2(float lo, float hi)
     return *reinterpret_cast<uint32_t *>(&p);
 }
 
+__device__ __forceinline__ long long az_min_ll(long long a, long long b) { return a < b ? a : b; }
+
 // table: bf16 [9][4][C] (tap-major; value 3 = off board = zeros), bias f32 [C].
 // Thread = (position lane, channel group of 8): 256 threads = (256 / groups)
 // positions x groups.  Table and a per-position offset list live in shared
@@ -202,9 +204,14 @@ k_nn_heads(const uint16_t *__restrict__ x, long long P, const float *__restrict_
 __global__ void __launch_bounds__(256)
 k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long long N,
                const uint16_t *__restrict__ table, const float *__restrict__ bias,
-               uint16_t *__restrict__ out)
+               uint16_t *__restrict__ out, const int *__restrict__ live)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // packed leaves (AZ_CFG_PACK_LEAVES): only the first *live rows of this batch hold boards.
+    // The groups they occupy are written whole -- rows past *live as empty boards -- so that the
+    // tower never runs over activations left behind by an earlier, larger batch.
+    const long long Nall = N;
+    if (live != nullptr) N = az_min_ll(N, (long long)*live);
     uint16_t *t3 = reinterpret_cast<uint16_t *>(smem_raw);              // [3 dy][64 codes][64 c]
     uint32_t *scode = reinterpret_cast<uint32_t *>(smem_raw + 3 * 64 * 64 * 2);      // [bpg][n][n]
     const int pn = n + 2, pn1 = n + 1, bpg = 128 / pn1, items = bpg * pn * pn, ncell = bpg * n * n;
@@ -264,7 +271,7 @@ k_nn_stem_slab(const int8_t *__restrict__ cells, int cell_stride, int n, long lo
             scode[i] = word;
         }
         __syncthreads();
-        const int left = (int)min((long long)bpg, N - g * bpg);
+        const int left = (int)min((long long)bpg, Nall - g * bpg);
         for (int y = 0; y < n; y++) {
             uint16_t *slab = out + (8 + (g * n + y) * 128) * 64;
 #pragma unroll
@@ -309,9 +316,11 @@ __device__ __forceinline__ void az_mma_bf16_16816(float (&c)[4], const uint32_t 
 template <int H>
 __global__ void __launch_bounds__(256)
 k_nn_heads_slab(const uint16_t *__restrict__ x, long long N, int n, const float *__restrict__ w,
-                const float *__restrict__ b, uint16_t *__restrict__ out, long long ostride)
+                const float *__restrict__ b, uint16_t *__restrict__ out, long long ostride,
+                const int *__restrict__ live)
 {
     static_assert(H <= 8 && (H & 1) == 0, "heads fit one n = 8 MMA tile");
+    if (live != nullptr) N = az_min_ll(N, (long long)*live);
     const int tid = threadIdx.x, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int pn1 = n + 1, bpg = 128 / pn1;
     // B fragments of column (head) g for the four k steps: step s covers channels
@@ -383,8 +392,9 @@ __global__ void __launch_bounds__(256)
 k_nn_tail(const uint16_t *__restrict__ y, long long N, int ld, int nfc2, int nn,
           const float *__restrict__ bias, const float *__restrict__ w3, const float *__restrict__ b3,
           float *__restrict__ value, long long value_stride,
-          float *__restrict__ logits, long long logits_stride)
+          float *__restrict__ logits, long long logits_stride, const int *__restrict__ live)
 {
+    if (live != nullptr) N = az_min_ll(N, (long long)*live);
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;

@@ -42,7 +42,7 @@ class Engine:
     def __init__(self, num_games, board_size=11, max_batch=10,
                  nodes_per_game=None, max_nodes_ref=10_000_000, replay_rows=0,
                  max_plies=300, seed=0, first_game_id=0, game_id_stride=0,
-                 device=None, soft_pool_full=False):
+                 device=None, soft_pool_full=False, pack_leaves=False):
         if device is None:
             device = torch.device('cuda', torch.cuda.current_device())
         device = torch.device(device)
@@ -66,7 +66,9 @@ class Engine:
             max_plies=int(max_plies), seed=int(seed) & (2 ** 64 - 1),
             first_game_id=int(first_game_id),
             game_id_stride=int(game_id_stride),
-            flags=_cabi.AZ_CFG_SOFT_POOL_FULL if soft_pool_full else 0)
+            flags=(_cabi.AZ_CFG_SOFT_POOL_FULL if soft_pool_full else 0)
+            | (_cabi.AZ_CFG_PACK_LEAVES if pack_leaves else 0))
+        self.pack_leaves = bool(pack_leaves)
         nbytes = self.lib.az_engine_device_bytes(C.byref(self.cfg))
         if nbytes == 0:
             raise ValueError('invalid engine configuration')
@@ -86,6 +88,8 @@ class Engine:
         self.counters = self._view(AZ_BUF_COUNTERS)
         self.leaf_moves = self._view(AZ_BUF_LEAF_MOVES)
         self.globals = self._view(AZ_BUF_GLOBALS)
+        # AZ_CFG_PACK_LEAVES: [g0] = live leaf rows of the window that starts at game g0
+        self.leaf_rows = self._view(_cabi.AZ_BUF_LEAF_ROWS)
         self.replay = self._view(AZ_BUF_REPLAY, torch.uint8) \
             if replay_rows else None
         self.cell_stride = self.leaf_board.shape[-1]

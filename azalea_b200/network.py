@@ -244,10 +244,13 @@ class HexNetwork(nn.Module):
 
     @torch.no_grad()
     def evaluate_cells(self, cells, value_out=None, logits_out=None,
-                       logits_stride=None, want_value=True):
+                       logits_stride=None, want_value=True, live_rows=None):
         """int8 [N, >= n*n] network-view boards -> value f32 [N], logits
         f32 [N, n*n] over tiles (no legal-move gather, no softmax).  The
-        optional outputs are written in place (see _evaluate_cells_tcgen05)."""
+        optional outputs are written in place (see _evaluate_cells_tcgen05).
+        ``live_rows``: int32 device tensor holding the number of leading rows
+        that hold boards (packed leaves, AZ_CFG_PACK_LEAVES); our kernels then
+        work on that many rows, the comparison arms ignore it and evaluate all N."""
         f = self._fast
         if f is None:
             raise RuntimeError('call prepare_inference() first')
@@ -259,7 +262,7 @@ class HexNetwork(nn.Module):
                 and cells.stride(1) == 1)
         if glue and self.tower == 'tcgen05' and f['tower'] is not None:
             return self._evaluate_cells_tcgen05(cells, value_out, logits_out,
-                                                logits_stride, want_value)
+                                                logits_stride, want_value, live_rows)
         if glue:
             # our kernels at both ends of the tower (csrc/az_nn_glue.cuh)
             from . import _cabi
@@ -325,7 +328,7 @@ class HexNetwork(nn.Module):
 
     @torch.no_grad()
     def _evaluate_cells_tcgen05(self, cells, value_out=None, logits_out=None,
-                                logits_stride=None, want_value=True):
+                                logits_stride=None, want_value=True, live_rows=None):
         """evaluate_cells with the whole tower on our tcgen05 convolution
         (csrc/az_tower.cuh): stem kernel -> 12 x az_nn_conv3x3 over the slab
         activation layout (residual added in the epilogue, in place) -> heads
@@ -359,8 +362,9 @@ class HexNetwork(nn.Module):
         x, y, flat, yfc, scratch = bufs
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _cabi.check(L.az_nn_stem(p(cells), cells.stride(0), n, N, p(f['stem_table']),
-                                 p(f['stem_bias']), p(x), 64, 1, stream))
+        live = p(live_rows) if live_rows is not None else None
+        _cabi.check(L.az_nn_stem_live(p(cells), cells.stride(0), n, N, p(f['stem_table']),
+                                      p(f['stem_bias']), p(x), 64, 1, live, stream))
         ev = getattr(self, 'conv_events', None)     # bench.py: per-launch CUDA events
         cur = torch.cuda.current_stream(dev)
 
@@ -377,8 +381,8 @@ class HexNetwork(nn.Module):
         if fused is not None and self.tower_fused >= 2:
             # the whole tower chained in one launch (csrc/az_block.cuh), in place
             wall, ball = f['tower_chain']
-            timed(lambda: _cabi.check(L.az_nn_resblocks(
-                p(x), p(wall), p(ball), p(scratch), n, npad, len(fused), stream)), 'chain%d' % len(fused))
+            timed(lambda: _cabi.check(L.az_nn_resblocks_live(
+                p(x), p(wall), p(ball), p(scratch), n, npad, len(fused), live, stream)), 'chain%d' % len(fused))
         elif fused is not None:
             # one launch per residual block, in place
             for w12, b12 in fused:
@@ -393,8 +397,8 @@ class HexNetwork(nn.Module):
         # head activations with the board row padded to a multiple of 8 (zeros):
         # the merged FC GEMM then runs a current cuBLAS kernel (K = 726 falls
         # back to a legacy one, 0.15 ms instead of 0.03)
-        _cabi.check(L.az_nn_heads(p(x), N * nn2, p(f['heads_w32']), p(f['heads_b32']),
-                                  p(flat), flat.shape[1], 64, 6, n, stream))
+        _cabi.check(L.az_nn_heads_live(p(x), N * nn2, p(f['heads_w32']), p(f['heads_b32']),
+                                       p(flat), flat.shape[1], 64, 6, n, live, stream))
         torch.mm(flat, f['fc_pad_t'], out=yfc)
         k2 = f['nfc2']
         if value_out is None and want_value:
@@ -403,8 +407,8 @@ class HexNetwork(nn.Module):
             logits_out = torch.empty(N, nn2, dtype=torch.float32, device=dev)
             logits_stride = nn2
         w3, b3 = f['value_fc3_32']
-        _cabi.check(L.az_nn_tail(
+        _cabi.check(L.az_nn_tail_live(
             p(yfc), N, yfc.shape[1], k2, n, p(f['fc_bias32']), p(w3), p(b3),
             p(value_out) if value_out is not None else None, 1,
-            p(logits_out), int(logits_stride or nn2), stream))
+            p(logits_out), int(logits_stride or nn2), live, stream))
         return value_out, logits_out

@@ -68,7 +68,7 @@ class LockstepSelfPlay:
                  move_sampling=True, move_exploration=True, seed=0,
                  device=None, rank=0, world_size=1, nodes_per_game=None,
                  replay_rows=None, collect_replay=True, cuda_graph=True,
-                 max_plies=300, random_play=False, streams=None):
+                 max_plies=300, random_play=False, streams=None, pack_leaves=None):
         # random_play: RandomPolicy self-play (random_policy.py:25-41) -- no
         # search, uniform move choice and uniform moves_prob at every ply;
         # how the reference fills the replay buffer before training
@@ -102,16 +102,23 @@ class LockstepSelfPlay:
                 self.G, self.nn, self.sims_per_move, device)
         # a full pool half never kills a game here: the expansion is skipped and
         # counted (AZ_CFG_SOFT_POOL_FULL); see counters()['pool_skipped_expansions']
+        # packed leaves (AZ_CFG_PACK_LEAVES): with a network in the loop the select kernel
+        # writes only the leaves that need it (unique, not terminal; mcts.py:75,192-200) as
+        # consecutive rows, and the evaluator works on that many -- default whenever the
+        # evaluator can take a device-side row count
+        self.is_stub = isinstance(evaluator, StubEvaluator)
+        if pack_leaves is None:
+            pack_leaves = not self.is_stub and hasattr(evaluator, 'evaluate_cells')
+        self.pack_leaves = bool(pack_leaves) and not self.is_stub
         self.eng = Engine(self.G, self.n, max_batch=self.batch,
                           nodes_per_game=nodes_per_game,
                           replay_rows=replay_rows, max_plies=max_plies,
                           seed=seed, first_game_id=rank * self.G,
                           game_id_stride=world_size * self.G, device=device,
-                          soft_pool_full=True)
+                          soft_pool_full=True, pack_leaves=self.pack_leaves)
         self.device = self.eng.device
         self.chosen = torch.zeros(self.G, 4, dtype=torch.int32,
                                   device=self.device)
-        self.is_stub = isinstance(evaluator, StubEvaluator)
         if not self.is_stub:
             if getattr(evaluator, '_fast', None) is None:
                 evaluator.eval()
@@ -152,9 +159,10 @@ class LockstepSelfPlay:
                 logits_stride=eng.max_batch * eng.nn, want_value=False)
             return None, None, _cabi.AZ_PRIOR_LOGITS
         cells = eng.leaf_board[g0:g1].view((g1 - g0) * eng.max_batch, eng.cell_stride)
+        kw = {'live_rows': eng.leaf_rows[g0:g0 + 1]} if self.pack_leaves else {}
         self.evaluator.evaluate_cells(
             cells, value_out=eng.value[g0:g1].view(-1),
-            logits_out=eng.prior[g0:g1].view(-1, eng.nn), logits_stride=eng.nn)
+            logits_out=eng.prior[g0:g1].view(-1, eng.nn), logits_stride=eng.nn, **kw)
         return None, None, _cabi.AZ_PRIOR_LOGITS
 
     def _window_body(self, g0, g1):

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define AZ_ABI_VERSION 2
+#define AZ_ABI_VERSION 3
 
 enum {
     AZ_OK = 0,
@@ -84,7 +84,18 @@ enum {
      * AZ_ST_POOL_FULL and dropping the game.  The reference never gets there
      * (one 1e7-node pool per game, search_tree.py:17-18); skipped expansions
      * are counted in AZ_CNT_POOL_SKIPPED. */
-    AZ_CFG_SOFT_POOL_FULL = 1
+    AZ_CFG_SOFT_POOL_FULL = 1,
+    /* Packed leaves.  The reference evaluates only the unique, non-terminal
+     * leaves of a batch (mcts.py:75,139-152,192-200); with this flag
+     * az_mcts_select writes exactly those, densely: the boards of a window's
+     * leaves go to rows [g0 * max_batch, g0 * max_batch + live) of
+     * AZ_BUF_LEAF_BOARD (g0 = first game of the window), live is left in
+     * AZ_BUF_LEAF_ROWS[g0], leaf_info[..][3] becomes depth | row << 10, and
+     * az_mcts_expand_backup reads value / prior of a leaf at its row and
+     * resets the count.  The evaluator (az_nn_*_live) then works on `live`
+     * rows instead of num_games * max_batch: duplicates and terminal leaves
+     * cost no network time.  Not for az_leaf_moves / host evaluators. */
+    AZ_CFG_PACK_LEAVES = 2
 };
 
 typedef struct az_engine az_engine;
@@ -92,7 +103,8 @@ typedef struct az_engine az_engine;
 /* buffers the caller may view inside its device block */
 enum {
     AZ_BUF_LEAF_BOARD = 0,  /* int8  [G][max_batch][cell_stride]  network-view cells 0/1/2 */
-    AZ_BUF_LEAF_INFO = 1,   /* int32 [G][max_batch][4] node(-1 = none), flags|colour<<8, num_moves, depth */
+    AZ_BUF_LEAF_INFO = 1,   /* int32 [G][max_batch][4] node(-1 = none), flags|colour<<8, num_moves, depth
+                               (AZ_CFG_PACK_LEAVES: depth | row << 10) */
     AZ_BUF_VALUE = 2,       /* f32   [G][max_batch]           evaluator output */
     AZ_BUF_PRIOR = 3,       /* f32   [G][max_batch][n*n]      evaluator output (priors or logits) */
     AZ_BUF_META = 4,        /* int32 [G][16] */
@@ -100,7 +112,9 @@ enum {
     AZ_BUF_COUNTERS = 6,    /* int64 [G][16] per-game counters (sum over games on the host) */
     AZ_BUF_LEAF_MOVES = 7,  /* int32 [G][max_batch][n*n] network-view legal moves, 0-padded */
     AZ_BUF_GLOBALS = 8,     /* int64 [16]: [0] = replay append cursor (rows) */
-    AZ_BUF__COUNT = 9
+    AZ_BUF_LEAF_ROWS = 9,   /* int32 [G]: [g0] = live leaf rows of the window starting at game g0
+                               (AZ_CFG_PACK_LEAVES) */
+    AZ_BUF__COUNT = 10
 };
 
 /* counter columns (AZ_BUF_COUNTERS); each game's warp owns its row, so the
@@ -343,6 +357,29 @@ int az_nn_resblock(void *x_dev, const void *w_dev, const float *bias_dev,
 int az_nn_resblocks(void *x_dev, const void *w_dev, const float *bias_dev,
                     void *scratch_dev, int board_size, int64_t num_boards,
                     int num_blocks, void *stream);
+/* The same four evaluator stages over a batch whose size is only known on the
+ * device (AZ_CFG_PACK_LEAVES): num_boards is the capacity the grids are sized
+ * for, *live_rows_dev (int32, device; NULL = num_boards) the number of leading
+ * rows that hold boards when the kernel runs.  Slab layout only.  The stem
+ * writes the groups the live rows occupy whole (rows past the count as empty
+ * boards), the tower and the heads run over those groups, the tail writes
+ * value / logits of the live rows; nothing else is touched. */
+int az_nn_stem_live(const int8_t *cells_dev, int cell_stride, int board_size,
+                    int64_t num_boards, const void *table_dev, const float *bias_dev,
+                    void *out_dev, int channels, int padded_layout,
+                    const int32_t *live_rows_dev, void *stream);
+int az_nn_resblocks_live(void *x_dev, const void *w_dev, const float *bias_dev,
+                         void *scratch_dev, int board_size, int64_t num_boards,
+                         int num_blocks, const int32_t *live_rows_dev, void *stream);
+int az_nn_heads_live(const void *x_dev, int64_t positions, const float *w_dev,
+                     const float *b_dev, void *out_dev, int64_t out_board_stride,
+                     int channels, int heads, int padded_board_size,
+                     const int32_t *live_rows_dev, void *stream);
+int az_nn_tail_live(const void *y_dev, int64_t num_boards, int ld, int nfc2,
+                    int board_size, const float *fc_bias_dev, const float *w3_dev,
+                    const float *b3_dev, float *value_dev, int64_t value_stride,
+                    float *logits_dev, int64_t logits_stride,
+                    const int32_t *live_rows_dev, void *stream);
 /* Diagnostic: how many two-CTA clusters az_nn_resblock sizes its grid for on
  * the current device (cudaOccupancyMaxActiveClusters; 74 on a B200), 0 before
  * the first launch. */

@@ -13,7 +13,7 @@ def test_library_loads_and_exports_all_declared_symbols():
     assert len(names) >= 24
     for name in names:
         assert hasattr(L, name), name
-    assert L.az_abi_version() == 2
+    assert L.az_abi_version() == 3
 
 
 def test_device_bytes_is_pure_host_arithmetic():

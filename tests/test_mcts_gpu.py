@@ -429,3 +429,59 @@ def test_play_game_reproduces_reference_game(golden_mcts, name):
     nodes = np.asarray(g[f'{name}/num_nodes'], dtype=np.float64)
     assert np.isclose(metrics['search_tree_nodes'], nodes.mean())
     assert np.isclose(metrics['search_value'], np.mean(g[f'{name}/search_value']), atol=1e-5)
+
+
+def test_packed_leaves_engine_level():
+    """AZ_CFG_PACK_LEAVES: az_mcts_select writes the leaves that need the
+    evaluator (unique, not terminal; mcts.py:75,139-152,192-200) as consecutive
+    rows of the window, leaf_info[..][3] = depth | row << 10, the count in
+    AZ_BUF_LEAF_ROWS[g0]; az_mcts_expand_backup reads value / prior at the row
+    and resets the count.  Same searches as the slot-indexed engine, bit for
+    bit, on full-board and windowed launches."""
+    from azalea_b200 import Engine
+    G, n, B, coef = 48, 5, 8, 0.5
+    nn = n * n
+    a = Engine(G, n, max_batch=B, seed=9)
+    b = Engine(G, n, max_batch=B, seed=9, pack_leaves=True)
+    gen = torch.Generator(device='cuda').manual_seed(1)
+    windows = [(0, 0), (0, 20), (20, 28)]       # whole engine, then two windows
+    for eng in (a, b):
+        eng.select_root(); eng.stub_eval(stubs.ROUGH); eng.expand_root()
+    for it in range(40):
+        w = windows[it % 3] if it >= 10 else (0, 0)
+        g0, cnt = w if w[1] else (0, G)
+        for eng in (a, b):
+            eng.set_window(*w)
+            eng.select(B, coef)
+        ia = a.leaf_info.cpu().numpy()[g0:g0 + cnt]
+        ib = b.leaf_info.cpu().numpy()[g0:g0 + cnt]
+        live = int(b.leaf_rows[g0].item())
+        need = (ia[..., 0] >= 0) & ((ia[..., 1] & 0xff) == 0)
+        assert live == int(need.sum()) and live > 0
+        assert (ia[..., :3] == ib[..., :3]).all()
+        assert ((ib[..., 3] & 1023) == ia[..., 3]).all()
+        rows = (ib[..., 3] >> 10)[need]
+        assert sorted(rows.tolist()) == list(range(live))       # dense, every row used once
+        # a game's leaves sit in consecutive rows, in slot order
+        ca = a.leaf_board.cpu().numpy()[g0:g0 + cnt].reshape(cnt * B, -1)
+        cb = b.leaf_board.cpu().numpy()[g0:g0 + cnt].reshape(cnt * B, -1)
+        assert (cb[rows] == ca[need.reshape(-1)]).all()
+        # evaluator outputs: slot-indexed for a, row-indexed for b
+        value = torch.rand(cnt * B, device='cuda', generator=gen) * 2 - 1
+        prior = torch.randn(cnt * B, nn, device='cuda', generator=gen)
+        a.value[g0:g0 + cnt].view(-1).copy_(value)
+        a.prior[g0:g0 + cnt].view(-1, nn).copy_(prior)
+        idx = torch.from_numpy(np.flatnonzero(need.reshape(-1))).cuda()
+        rt = torch.from_numpy(rows.astype(np.int64)).cuda()
+        b.value[g0:g0 + cnt].view(-1)[rt] = value[idx]
+        b.prior[g0:g0 + cnt].view(-1, nn)[rt] = prior[idx]
+        for eng in (a, b):
+            eng.expand_backup(None, None, 1)
+        assert int(b.leaf_rows[g0].item()) == 0
+        for eng in (a, b):
+            eng.set_window(0, 0)
+        sa, sb = a.root_stats(), b.root_stats()
+        for x, y in zip(sa, sb):
+            assert torch.equal(x, y)
+    assert (a.status().cpu().numpy() == 0).all() and (b.status().cpu().numpy() == 0).all()
+    assert a.counter_totals() == b.counter_totals()

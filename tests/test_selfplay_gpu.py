@@ -805,3 +805,60 @@ def test_play_commit_temperature_zero_is_uniform_over_the_ties():
     chi2 = float(((obs - exp) ** 2 / exp).sum())
     dof = len(top) - 1
     assert chi2 < dof + 5 * np.sqrt(2 * dof), (chi2, dof)
+
+
+@pytest.mark.parametrize('streams,graph', ((1, False), (2, False), (2, True)))
+def test_packed_leaves_do_not_change_the_games(streams, graph):
+    """LockstepSelfPlay packs the leaves by default when a network evaluates
+    them (AZ_CFG_PACK_LEAVES: duplicates and terminal leaves cost no network
+    time).  A row's evaluation does not depend on where in the batch it sits,
+    so moves and replay rows are identical to the slot-indexed run -- 6x64
+    network on our kernels, small searches near the end of 5x5 games (many
+    duplicate and terminal leaves)."""
+    from azalea_b200 import LockstepSelfPlay
+    from azalea_b200.network import HexNetwork
+
+    def play(pack, streams, graph):
+        torch.manual_seed(0)
+        net = HexNetwork(5, 2, 64).eval().cuda()
+        net.prepare_inference(torch.bfloat16)
+        assert net.tower == 'tcgen05'
+        sp = LockstepSelfPlay(net, num_games=96, board_size=5, simulations=40,
+                              search_batch_size=8, seed=5, streams=streams,
+                              cuda_graph=graph, pack_leaves=pack)
+        assert sp.pack_leaves == pack
+        chosen = []
+        for _ in range(30):
+            sp.step_move()
+            chosen.append(sp.chosen.cpu().numpy().copy())
+        assert (sp.eng.status().cpu().numpy() == 0).all()
+        return np.stack(chosen), sp.harvest(), sp.counters()
+    c0, r0, n0 = play(False, 1, False)
+    c1, r1, n1 = play(True, streams, graph)
+    assert n1['nn_rows'] < n1['simulations']        # there was something to skip
+    assert np.array_equal(c0, c1)
+    assert r0.shape == r1.shape and np.array_equal(r0, r1)
+    assert n0 == n1
+
+
+def test_evaluator_live_rows():
+    """az_nn_*_live: with a device-side row count the evaluator's outputs for
+    the live rows equal the full evaluation's, the rows past the count are
+    left alone, and a count of zero runs (clusters without a group)."""
+    from azalea_b200.network import HexNetwork
+    torch.manual_seed(1)
+    n, N = 11, 700
+    net = HexNetwork(n, 3, 64).eval().cuda()
+    net.prepare_inference(torch.bfloat16)
+    cells = torch.zeros(N, 128, dtype=torch.int8, device='cuda')
+    cells[:, :n * n] = torch.randint(0, 3, (N, n * n), device='cuda', dtype=torch.int8)
+    v0, l0 = net.evaluate_cells(cells)
+    v0, l0 = v0.clone(), l0.clone()
+    for live in (N, 699, 345, 10, 1, 0):
+        cnt = torch.tensor([live], dtype=torch.int32, device='cuda')
+        v = torch.full((N,), 7.0, device='cuda')
+        lg = torch.full((N, n * n), 7.0, device='cuda')
+        net.evaluate_cells(cells, value_out=v, logits_out=lg, logits_stride=n * n, live_rows=cnt)
+        torch.cuda.synchronize()
+        assert torch.equal(v[:live], v0[:live]) and torch.equal(lg[:live], l0[:live]), live
+        assert (v[live:] == 7.0).all() and (lg[live:] == 7.0).all(), live

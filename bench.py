@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument('--nodes-per-game', type=int, default=0)
     ap.add_argument('--streams', type=int, default=2,
                     help='windows of the games driven on separate streams (network evaluator; DESIGN.md 5)')
+    ap.add_argument('--pack-leaves', type=int, default=1,
+                    help='1: the evaluator runs on the packed unique non-terminal leaves (default); '
+                         '0: on every leaf slot (A/B)')
     ap.add_argument('--preroll', type=int, default=110,
                     help='stagger the games before the steady-state window: slot g is advanced by '
                          'g * PREROLL / G random plies (0 = time the opening only)')
@@ -337,7 +340,8 @@ def run_ours(args):
                           device=dev, cuda_graph=not args.no_graph,
                           collect_replay=True,
                           streams=args.streams if args.evaluator == 'net' else 1,
-                          nodes_per_game=args.nodes_per_game or None, **SEARCH)
+                          nodes_per_game=args.nodes_per_game or None,
+                          pack_leaves=bool(args.pack_leaves) and args.evaluator == 'net', **SEARCH)
     G, per_move = args.games, sp.sims_per_move
     n_streams = sp.streams
     steps = args.steps
@@ -467,13 +471,17 @@ def run_ours(args):
     roofline_tree = None
     if conv_ev:
         roofline_tree = roofline
+        live_frac = dk['nn_rows'] / (launches * G * sp.batch) if sp.pack_leaves else 1.0
         roofline = tower_roofline(conv_ev, args.board, G * sp.batch, ms / steps, hbm_peak,
-                                  bf16_peak, peak_src, 'bf16_tflops_sustained' in peaks, tj)
+                                  bf16_peak, peak_src, 'bf16_tflops_sustained' in peaks, tj, live_frac)
+        roofline['rows_per_launch'] = live_frac * G * sp.batch
+        roofline['packed_leaves'] = bool(sp.pack_leaves)
     nn_info = None
     if args.evaluator == 'net':
         step_ms = ms / steps
         rows = d_run['nn_rows'] / steps
-        padded = G * (per_move + 1)
+        # rows the evaluator runs over: every leaf slot, or the packed live rows (+ the roots)
+        padded = G * (per_move + 1) if not sp.pack_leaves else rows + G
         flop = NN_FLOP_PER_LEAF.get(args.board)
         if flop:
             nn_ms = step_ms - (sel_ms + exp_ms)
@@ -596,7 +604,7 @@ def guarded(fn):
 
 
 def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_src,
-                   tensor_measured, tj):
+                   tensor_measured, tj, live_frac=1.0):
     """Roofline of the step's dominant kernel, the evaluator's tower
     convolutions, from per-launch CUDA events.
 
@@ -607,9 +615,11 @@ def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_sr
     residual launch 3."""
     cell_bytes = board * board * 128
     conv_flop = board * board * 2 * 64 * 576
+    # packed leaves: a search batch's launch runs over its live rows only (device-side count);
+    # live_frac = rows the network had to evaluate / leaf slots, from the device counters
     kinds = {}
     for e0, e1, kind, nb in conv_ev:
-        kinds.setdefault(kind, []).append((e0.elapsed_time(e1), nb))
+        kinds.setdefault(kind, []).append((e0.elapsed_time(e1), nb * live_frac if nb == boards else nb))
     tot_ms = sum(t for v in kinds.values() for t, _ in v)
     n_launch = sum(len(v) for v in kinds.values())
     units = {'plain': 2, 'residual': 3, 'block': 2}

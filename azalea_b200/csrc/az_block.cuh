@@ -145,6 +145,38 @@ static_assert(!AZB_P_ASYNC || AZB_SY % 2 == 0, "st.async variant: a stage of C's
 
 #define AZB_MAXPASS 8       // residual blocks one launch can chain (their biases sit in shared memory)
 
+// FUSED HEADS (az_nn_resblocks_heads_live): the network's two 1x1 head convolutions (+ BN + ReLU;
+// 64 -> 2 + 4 channels, network.py:75-76,82-83) read the tower's output and nothing else does,
+// so C's epilogue of the LAST pass computes them from the rows it has just rounded to bf16:
+// thread = row holds 32 of the 64 channels, 6 x 32 FMAs against weights in CONSTANT memory (an
+// operand fetch through the constant cache: the shared-memory port, which bounds this kernel,
+// is not touched), the two halves of a row meet through 3 KB of shared memory, and the six bf16
+// head activations of the cell go straight into the [board][n*n*6 (+ pad)] rows the merged FC
+// GEMM reads.  Saves the separate heads launch and its pass over the activations.
+#define AZB_HEADS 6
+#define AZB_HEAD_FLOATS (AZB_HEADS * AZT_C + 8)     // [6][64] weights, then 6 biases
+// ONE weight set at a fixed address, so that every weight is an immediate constant-bank operand of
+// its FMA (a register-indexed LDC per weight made the last pass 65 % slower).  The launcher copies the
+// caller's weights here in stream order before every launch: launches on one stream may alternate
+// networks; launches that run CONCURRENTLY on several streams must use the same network (the two
+// windows of LockstepSelfPlay do).
+__constant__ float azb_heads_c[AZB_HEAD_FLOATS];
+
+// channels HALF * 32 + CHUNK * 8 .. + 8 of a row (bf16 pairs in ow) against the six head filters
+template <int HALF, int CHUNK>
+__device__ __forceinline__ void azb_heads_acc(const uint32_t (&ow)[4], float (&hacc)[AZB_HEADS])
+{
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const float a0 = __uint_as_float(ow[q] << 16), a1 = __uint_as_float(ow[q] & 0xffff0000u);
+        constexpr int c0 = HALF * 32 + CHUNK * 8;
+#pragma unroll
+        for (int hh = 0; hh < AZB_HEADS; hh++)
+            hacc[hh] = __fmaf_rn(a1, azb_heads_c[hh * AZT_C + c0 + 2 * q + 1],
+                                 __fmaf_rn(a0, azb_heads_c[hh * AZT_C + c0 + 2 * q], hacc[hh]));
+    }
+}
+
 struct azb_params {
     uint8_t *x;             // activations, slab layout, pre-swizzled; updated in place
     const uint8_t *w;       // [passes][2 layers][3 dx][192 = dy*64 + c_out][128 B] pre-swizzled weights
@@ -155,6 +187,9 @@ struct azb_params {
     int passes;             // residual blocks to apply, one after the other (1 .. AZB_MAXPASS)
     uint8_t *scratch;       // AZB_VIA_L2: [clusters][AZB_R][16 KB] hand-over ring in global memory
     unsigned long long *prof;   // probe only: per-role wait cycles of cluster 0 ([rank][32]) or NULL
+    uint16_t *heads_out;    // fused heads: bf16 [boards][heads_stride] (6 per cell, cell-major), or NULL
+    long long heads_stride; // elements between two boards' rows
+    long long heads_boards; // rows of heads_out
     const int *live;        // packed leaves: device count of boards that are live in this batch (or NULL: all)
     int debug;              // probe only (tools/probe/block_time.py): 2 = C skips its global stores,
                             // 4 = C skips the residual loads, 8 = no MMAs
@@ -315,6 +350,7 @@ k_resblock(const azb_params p)
     __shared__ uint32_t tmem_holder;
     __shared__ volatile uint32_t s_stored;          // output slabs (index t) whose store has completed
     __shared__ __align__(16) float s_bias[AZB_MAXPASS * AZT_C];     // this CTA's layer of every pass
+    __shared__ float s_hx[2][2][AZB_HEADS * 128];   // fused heads: partial sums of channels 0..31, [group][slab parity]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool prof_on = AZB_PROF && p.prof != nullptr && (blockIdx.x >> 1) == 0 && lane == 0;
@@ -695,11 +731,15 @@ k_resblock(const azb_params p)
         const bool real = l < p.bpg * (n + 1) && (l % (n + 1)) != n;    // not a pad cell
         const uint32_t keep = real ? 0xffffffffu : 0u;
         const int sw = l & 7;                                       // == R & 7 (8 + 128 q + l)
+        const bool do_heads = !isP && p.heads_out != nullptr;
+        const int hbl = l / (n + 1), hbx = l - hbl * (n + 1);       // this row's board of the group and column
         azb_pos at = {grp, grp, 0};
         at.advance(0, nslabs);
         for (int y = grp % n; at.t < NT; at.advance(2, nslabs), y = (y + 2) % n) {
             const int t = at.t, sb = t % T;
             const float *bias = s_bias + at.pass * AZT_C;
+            const bool hpass = do_heads && at.pass == p.passes - 1;
+            float hacc[AZB_HEADS] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             uint4 *srow = reinterpret_cast<uint4 *>(s_out + sb * AZT_OUT_BYTES + l * AZT_ROW);
             uint4 rv[4];
             if (!isP && !(p.debug & 4)) {
@@ -774,6 +814,20 @@ k_resblock(const azb_params p)
                         ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
                     }
                     o[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                    if (hpass) {
+                        // the head convolutions see the bf16 activations the tower stores
+                        if (half == 0) {
+                            if (h == 0 && g == 0) azb_heads_acc<0, 0>(ow, hacc);
+                            if (h == 0 && g == 1) azb_heads_acc<0, 1>(ow, hacc);
+                            if (h == 1 && g == 0) azb_heads_acc<0, 2>(ow, hacc);
+                            if (h == 1 && g == 1) azb_heads_acc<0, 3>(ow, hacc);
+                        } else {
+                            if (h == 0 && g == 0) azb_heads_acc<1, 0>(ow, hacc);
+                            if (h == 0 && g == 1) azb_heads_acc<1, 1>(ow, hacc);
+                            if (h == 1 && g == 0) azb_heads_acc<1, 2>(ow, hacc);
+                            if (h == 1 && g == 1) azb_heads_acc<1, 3>(ow, hacc);
+                        }
+                    }
                     // chunk c8 of the row, at its swizzled place in the staging tile / in C's stage
                     if (AZB_P_ASYNC && isP) azb_st_async(ybase + (uint32_t)((c8 ^ sw) << 4), o[g], ybar);
                     else srow[c8 ^ sw] = o[g];
@@ -789,6 +843,37 @@ k_resblock(const azb_params p)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) azt_mbar_arrive(&bar_out_done[sb]);
+            }
+            if (hpass) {
+                // the warps with channels 0..31 hand their partial sums to the warps with channels
+                // 32..63 of the same rows (named barrier 5 + group, all eight warps); two buffers by
+                // slab parity, so the readers of one slab and the writers of the next never meet
+                float *hx = s_hx[grp][(t >> 1) & 1];
+                if (half == 0) {
+#pragma unroll
+                    for (int hh = 0; hh < AZB_HEADS; hh++) hx[hh * 128 + l] = hacc[hh];
+                    // (both halves wait: an arrive-only producer two slabs ahead would complete the
+                    // barrier on its own)
+                    if (grp == 0) asm volatile("bar.sync 5, 256;" ::: "memory");
+                    else asm volatile("bar.sync 6, 256;" ::: "memory");
+                } else {
+                    if (grp == 0) asm volatile("bar.sync 5, 256;" ::: "memory");
+                    else asm volatile("bar.sync 6, 256;" ::: "memory");
+                    const long long board = (g0 + at.j / n) * p.bpg + hbl;
+                    float v[AZB_HEADS];
+#pragma unroll
+                    for (int hh = 0; hh < AZB_HEADS; hh++)
+                        v[hh] = fmaxf(hx[hh * 128 + l] + hacc[hh] + azb_heads_c[AZB_HEADS * AZT_C + hh], 0.f);
+                    if (real && board < p.heads_boards) {
+                        uint32_t *dst = reinterpret_cast<uint32_t *>(
+                            p.heads_out + board * p.heads_stride + (long long)(y * n + hbx) * AZB_HEADS);
+#pragma unroll
+                        for (int hh = 0; hh < AZB_HEADS; hh += 2) {
+                            __nv_bfloat162 pr = __floats2bfloat162_rn(v[hh], v[hh + 1]);
+                            dst[hh >> 1] = *reinterpret_cast<uint32_t *>(&pr);
+                        }
+                    }
+                }
             }
             if (prof_on) prof_acc[3] += clock64() - tb_;
         }

@@ -267,6 +267,43 @@ class Engine:
         """Rows waiting in the replay buffer (syncs)."""
         return int(self.globals[0].item())
 
+    @staticmethod
+    def _sort_rows(rows):
+        # finished games append in warp-scheduling order: sort by
+        # (game id, ply) so the output is deterministic
+        if len(rows):
+            key = rows[:, :12].copy().view([('g', '<i8'), ('p', '<i4')]).reshape(-1)
+            rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
+        return rows
+
+    def harvest_begin(self, pinned_bytes=64 << 20):
+        """First half of a pipelined harvest: read the row count (the only
+        sync), enqueue the rows' copy into pinned host memory and the clear,
+        and return a handle.  The caller may enqueue the next move before
+        ``harvest_end(handle)`` waits for the copy, so the host's share of the
+        harvest runs under that move."""
+        if self.replay is None:
+            raise RuntimeError('engine was created with replay_rows=0')
+        count = min(self.replay_count(), self.replay.shape[0])
+        cap = max(1, int(pinned_bytes) // self.row_bytes)
+        if count > cap:
+            return ('sync', self.harvest_replay())
+        if getattr(self, '_pinned_rows', None) is None or self._pinned_rows.shape[0] < cap:
+            self._pinned_rows = torch.empty(cap, self.row_bytes, dtype=torch.uint8).pin_memory()
+        self._pinned_rows[:count].copy_(self.replay[:count], non_blocking=True)
+        self.replay_clear()
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return ('async', count, done)
+
+    def harvest_end(self, handle):
+        """Second half: the rows of ``harvest_begin`` (host, sorted)."""
+        if handle[0] == 'sync':
+            return handle[1]
+        _, count, done = handle
+        done.synchronize()
+        return self._sort_rows(self._pinned_rows[:count].numpy().copy())
+
     def harvest_replay(self):
         """Copy the finished games' rows to the host and clear the buffer."""
         if self.replay is None:
@@ -274,12 +311,7 @@ class Engine:
         count = min(self.replay_count(), self.replay.shape[0])
         rows = self.replay[:count].cpu().numpy()
         self.replay_clear()
-        # finished games append in warp-scheduling order: sort by
-        # (game id, ply) so the output is deterministic
-        if len(rows):
-            key = rows[:, :12].copy().view([('g', '<i8'), ('p', '<i4')]).reshape(-1)
-            rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
-        return rows
+        return self._sort_rows(rows)
 
 
 def decode_replay_rows(rows, board_size):

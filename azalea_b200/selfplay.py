@@ -276,6 +276,15 @@ class LockstepSelfPlay:
             rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
         return rows
 
+    def harvest_begin(self):
+        """Pipelined harvest, first half (single process): sync on the row
+        count, enqueue the copy to pinned memory and the clear.  Enqueue the
+        next ``step_move()`` before calling ``harvest_end``."""
+        return self.eng.harvest_begin()
+
+    def harvest_end(self, handle):
+        return self.eng.harvest_end(handle)
+
     def counters(self):
         return self.eng.counter_totals()
 

@@ -387,18 +387,36 @@ def run_ours(args):
     chosen_host = torch.zeros(G, 4, dtype=torch.int32).pin_memory()
     sp.harvest(gather=world > 1)        # untimed: first use sets up the exchange
     barrier()
-    t0 = time.perf_counter()
-    rows_out = 0
-    for _ in range(steps):
+    def upload():
+        # the trainer's hand-off: weights from pinned host memory, inference tensors rebuilt
         if host_w:
             with torch.no_grad():
                 for p, w in zip(evaluator.parameters(), host_w):
                     p.copy_(w, non_blocking=True)
             evaluator.prepare_inference(torch.bfloat16)
-            h2d += h2d_step
-        sp.step_move()
+        return h2d_step
+
+    # The host loop is software-pipelined (every step still has its own upload and its own
+    # read-back inside the timed region): step k+1's weights are enqueued behind step k, so the
+    # host's launches run while the GPU plays step k; after the one sync on step k's row count the
+    # rows' copy, the clear and step k+1 are enqueued, and the rows are sorted under step k+1.
+    t0 = time.perf_counter()
+    rows_out = 0
+    h2d += upload()
+    sp.step_move()
+    for k in range(steps):
         chosen_host.copy_(sp.chosen, non_blocking=True)
-        rows = sp.harvest(gather=world > 1)  # syncs; D2H of finished games' rows (rank 0 gets all)
+        if k + 1 < steps:
+            h2d += upload()
+        if world > 1:
+            rows = sp.harvest(gather=True)      # syncs; rows of all ranks to rank 0 over NCCL
+            if k + 1 < steps:
+                sp.step_move()
+        else:
+            handle = sp.harvest_begin()         # syncs on the row count only
+            if k + 1 < steps:
+                sp.step_move()
+            rows = sp.harvest_end(handle)
         rows_out += len(rows)
         d2h += chosen_host.numel() * 4 + rows.nbytes + 8
     barrier()

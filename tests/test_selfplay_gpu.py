@@ -902,3 +902,25 @@ def test_fused_heads_match_heads_kernel(n, N):
     tol = 2.0 ** -7 * wv.abs().clamp(min=2.0 ** -6)      # one bf16 ulp
     assert (diff <= tol).all(), float(diff.max())
     assert (diff > 0).float().mean() < 0.02
+
+
+def test_pipelined_harvest_equals_harvest():
+    """harvest_begin / harvest_end (count sync, copy to pinned memory and clear
+    enqueued, the next move launched before the rows are waited for) return
+    the same rows as harvest(), move by move."""
+    from azalea_b200 import LockstepSelfPlay, StubEvaluator
+    def make():
+        return LockstepSelfPlay(StubEvaluator(2), num_games=64, board_size=5, simulations=30,
+                                search_batch_size=6, seed=4, cuda_graph=False)
+    a, b = make(), make()
+    got, want = [], []
+    b.step_move()
+    for k in range(40):
+        a.step_move()
+        want.append(a.harvest())
+        h = b.harvest_begin()
+        b.step_move()                   # the next move is in flight while the rows come back
+        got.append(b.harvest_end(h))
+    assert sum(len(r) for r in want) > 200
+    for r0, r1 in zip(want, got):
+        assert r0.shape == r1.shape and np.array_equal(r0, r1)

@@ -666,7 +666,9 @@ def tower_roofline(conv_ev, board, boards, step_ms, hbm_peak, bf16_peak, peak_sr
     key = ('k_resblock' if fused else 'k_conv3x3')
     try:
         ent = tj[key][f'{board}x{board}/{boards}' + (f'/chain{chain}' if chain else '')]
-        out['traffic'] = ent['traffic_bytes']
+        # the capture is a launch over all `boards` rows; a packed-leaves launch moves live_frac of it
+        out['traffic'] = ent['traffic_bytes'] * live_frac
+        out['traffic_source'] = ent.get('profile')
     except Exception:
         out['traffic'] = None
     if chain:

@@ -703,8 +703,7 @@ k_resblock(const azb_params p)
                     for (int q = 0; q < 4; q++) {
                         f[2 * q] += __uint_as_float(rw[q] << 16);
                         f[2 * q + 1] += __uint_as_float(rw[q] & 0xffff0000u);
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
+                        ow[q] = azt_relu_bf16x2(f[2 * q], f[2 * q + 1]) & keep;
                     }
                     R[c8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }
@@ -810,8 +809,7 @@ k_resblock(const azb_params p)
                     uint32_t ow[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
+                        ow[q] = azt_relu_bf16x2(f[2 * q], f[2 * q + 1]) & keep;
                     }
                     o[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                     if (hpass) {

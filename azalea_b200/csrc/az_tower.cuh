@@ -101,6 +101,15 @@ struct azt_params {
 
 __device__ __forceinline__ uint32_t azt_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ReLU + round to bf16 of two values in one instruction (lo in bits 0..15); the bits of
+// __floats2bfloat162_rn(fmaxf(lo, 0), fmaxf(hi, 0)) for every finite input
+__device__ __forceinline__ uint32_t azt_relu_bf16x2(float lo, float hi)
+{
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 __device__ __forceinline__ void azt_mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(azt_smem(bar)), "r"(count));
@@ -429,8 +438,7 @@ k_conv3x3(const azt_params p)
                     uint32_t ow[4];
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
-                        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(f[2 * q], 0.f), fmaxf(f[2 * q + 1], 0.f));
-                        ow[q] = *reinterpret_cast<uint32_t *>(&hh) & keep;
+                        ow[q] = azt_relu_bf16x2(f[2 * q], f[2 * q + 1]) & keep;
                     }
                     srow[c8 ^ sw] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                 }

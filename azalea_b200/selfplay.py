@@ -276,13 +276,36 @@ class LockstepSelfPlay:
             rows = rows[np.argsort(key, order=('g', 'p'), kind='stable')]
         return rows
 
-    def harvest_begin(self):
-        """Pipelined harvest, first half (single process): sync on the row
-        count, enqueue the copy to pinned memory and the clear.  Enqueue the
-        next ``step_move()`` before calling ``harvest_end``."""
-        return self.eng.harvest_begin()
+    def harvest_begin(self, gather=False):
+        """Pipelined harvest, first half: sync on the row count(s), enqueue
+        the exchange (``gather=True``: every rank's rows to rank 0 over NCCL),
+        the copy to pinned memory and the clear.  Enqueue the next
+        ``step_move()`` before calling ``harvest_end``, so the host's share of
+        the harvest runs under that move."""
+        if not gather:
+            return self.eng.harvest_begin()
+        import torch.distributed as dist
+        eng = self.eng
+        count = min(eng.replay_count(), eng.replay.shape[0])
+        rows = gather_replay_rows(eng.replay[:count])
+        eng.replay_clear()
+        if rows is None or (dist.is_initialized() and dist.get_rank() != 0):
+            return ('sync', np.zeros((0, eng.row_bytes), dtype=np.uint8))
+        n = rows.shape[0]
+        pinned = getattr(self, '_pinned_gather', None)
+        if pinned is None or pinned.shape[0] < n:
+            pinned = torch.empty(max(2 * n, 1 << 15), eng.row_bytes, dtype=torch.uint8).pin_memory()
+            self._pinned_gather = pinned
+        pinned[:n].copy_(rows, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return ('gathered', n, done, rows)      # (rows: kept alive until the copy has run)
 
     def harvest_end(self, handle):
+        if handle[0] == 'gathered':
+            _, n, done, _ = handle
+            done.synchronize()
+            return Engine._sort_rows(self._pinned_gather[:n].numpy().copy())
         return self.eng.harvest_end(handle)
 
     def counters(self):

@@ -386,10 +386,7 @@ def run_ours(args):
         host_w, h2d_step = [], 0
     chosen_host = torch.zeros(G, 4, dtype=torch.int32).pin_memory()
     # untimed: first use sets up the exchange (NCCL communicator / the pinned row buffer)
-    if world > 1:
-        sp.harvest(gather=True)
-    else:
-        sp.harvest_end(sp.harvest_begin())
+    sp.harvest_end(sp.harvest_begin(gather=world > 1))
     barrier()
     def upload():
         # the trainer's hand-off: weights from pinned host memory, inference tensors rebuilt
@@ -424,12 +421,9 @@ def run_ours(args):
             if k + 1 < nsteps:
                 up += upload()
             c1 = time.perf_counter()
-            if world > 1:
-                rows = sp.harvest(gather=True)      # syncs; rows of all ranks to rank 0 over NCCL
-                if k + 1 < nsteps:
-                    move(k + 1)
-            else:
-                handle = sp.harvest_begin()         # syncs on the row count only
+            if True:
+                # syncs on the row count(s) only; world > 1: rows of all ranks to rank 0 over NCCL
+                handle = sp.harvest_begin(gather=world > 1)
                 c2 = time.perf_counter()
                 if k + 1 < nsteps:
                     move(k + 1)

@@ -421,18 +421,17 @@ def run_ours(args):
             if k + 1 < nsteps:
                 up += upload()
             c1 = time.perf_counter()
-            if True:
-                # syncs on the row count(s) only; world > 1: rows of all ranks to rank 0 over NCCL
-                handle = sp.harvest_begin(gather=world > 1)
-                c2 = time.perf_counter()
-                if k + 1 < nsteps:
-                    move(k + 1)
-                c3 = time.perf_counter()
-                rows = sp.harvest_end(handle)
-                if dbg:
-                    print('e2e step %d: upload %.2f ms, harvest_begin %.2f, launch %.2f, harvest_end %.2f (host)'
-                          % (k, (c1 - c0) * 1e3, (c2 - c1) * 1e3, (c3 - c2) * 1e3,
-                             (time.perf_counter() - c3) * 1e3), file=sys.stderr)
+            # syncs on the row count(s) only; world > 1: rows of all ranks to rank 0 over NCCL
+            handle = sp.harvest_begin(gather=world > 1)
+            c2 = time.perf_counter()
+            if k + 1 < nsteps:
+                move(k + 1)
+            c3 = time.perf_counter()
+            rows = sp.harvest_end(handle)
+            if dbg:
+                print('e2e step %d: upload %.2f ms, harvest_begin %.2f, launch %.2f, harvest_end %.2f (host)'
+                      % (k, (c1 - c0) * 1e3, (c2 - c1) * 1e3, (c3 - c2) * 1e3,
+                         (time.perf_counter() - c3) * 1e3), file=sys.stderr)
             rows_out += len(rows)
             down += chosen_host.numel() * 4 + rows.nbytes + 8
         return rows_out, up, down, ev

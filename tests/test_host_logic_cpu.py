@@ -333,3 +333,23 @@ def test_distributed_refill_protocol_two_ranks_gloo():
         assert (rows[:, 2] == (12 * (step + 1)) % 251).all()
     served, w, mean, tracked = got[1][0]
     assert served == 3 and (w == 3.0).all() and (mean == 1.0).all() and tracked == 2
+
+
+def test_harvest_rows_are_sorted_by_game_and_ply():
+    """Finished games append their rows in warp-scheduling order; every harvest
+    path (harvest, harvest_begin / harvest_end, gathered) hands them out sorted
+    by (game id, ply) through Engine._sort_rows."""
+    import numpy as np
+    from azalea_b200.engine import Engine, ROW_HEADER
+    rng = np.random.RandomState(0)
+    rows = np.zeros((200, 64), dtype=np.uint8)
+    h = rows[:, :ROW_HEADER.itemsize].view(ROW_HEADER).reshape(-1)
+    h['game_id'] = rng.randint(0, 7, size=200) + (1 << 33)
+    h['ply'] = rng.randint(0, 50, size=200)
+    rows[:, 60] = np.arange(200) % 251
+    out = Engine._sort_rows(rows.copy())
+    ho = out[:, :ROW_HEADER.itemsize].copy().view(ROW_HEADER).reshape(-1)
+    key = list(zip(ho['game_id'].tolist(), ho['ply'].tolist()))
+    assert key == sorted(key)
+    assert sorted(map(bytes, out)) == sorted(map(bytes, rows))
+    assert len(Engine._sort_rows(rows[:0])) == 0

@@ -294,7 +294,8 @@ class LockstepSelfPlay:
         n = rows.shape[0]
         pinned = getattr(self, '_pinned_gather', None)
         if pinned is None or pinned.shape[0] < n:
-            pinned = torch.empty(max(2 * n, 1 << 15), eng.row_bytes, dtype=torch.uint8).pin_memory()
+            # (a first call may find everything the warm-up left behind: grow by a quarter, not by two)
+            pinned = torch.empty(max(n + n // 4, 1 << 15), eng.row_bytes, dtype=torch.uint8).pin_memory()
             self._pinned_gather = pinned
         pinned[:n].copy_(rows, non_blocking=True)
         done = torch.cuda.Event()

@@ -431,7 +431,8 @@ def test_play_game_reproduces_reference_game(golden_mcts, name):
     assert np.isclose(metrics['search_value'], np.mean(g[f'{name}/search_value']), atol=1e-5)
 
 
-def test_packed_leaves_engine_level():
+@pytest.mark.parametrize('G,n,B', ((48, 5, 8), (6, 19, 10), (1, 11, 10), (33, 3, 16)))
+def test_packed_leaves_engine_level(G, n, B):
     """AZ_CFG_PACK_LEAVES: az_mcts_select writes the leaves that need the
     evaluator (unique, not terminal; mcts.py:75,139-152,192-200) as consecutive
     rows of the window, leaf_info[..][3] = depth | row << 10, the count in
@@ -439,12 +440,13 @@ def test_packed_leaves_engine_level():
     and resets the count.  Same searches as the slot-indexed engine, bit for
     bit, on full-board and windowed launches."""
     from azalea_b200 import Engine
-    G, n, B, coef = 48, 5, 8, 0.5
+    coef = 0.5
     nn = n * n
     a = Engine(G, n, max_batch=B, seed=9)
     b = Engine(G, n, max_batch=B, seed=9, pack_leaves=True)
     gen = torch.Generator(device='cuda').manual_seed(1)
-    windows = [(0, 0), (0, 20), (20, 28)]       # whole engine, then two windows
+    # whole engine, then two windows
+    windows = [(0, 0), (0, G // 2), (G // 2, G - G // 2)] if G >= 4 else [(0, 0)] * 3
     for eng in (a, b):
         eng.select_root(); eng.stub_eval(stubs.ROUGH); eng.expand_root()
     for it in range(40):
@@ -457,7 +459,7 @@ def test_packed_leaves_engine_level():
         ib = b.leaf_info.cpu().numpy()[g0:g0 + cnt]
         live = int(b.leaf_rows[g0].item())
         need = (ia[..., 0] >= 0) & ((ia[..., 1] & 0xff) == 0)
-        assert live == int(need.sum()) and live > 0
+        assert live == int(need.sum()) and (live > 0 or n == 3)     # (3x3 games end within the search)
         assert (ia[..., :3] == ib[..., :3]).all()
         assert ((ib[..., 3] & 1023) == ia[..., 3]).all()
         rows = (ib[..., 3] >> 10)[need]

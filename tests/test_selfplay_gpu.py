@@ -924,3 +924,28 @@ def test_pipelined_harvest_equals_harvest():
     assert sum(len(r) for r in want) > 200
     for r0, r1 in zip(want, got):
         assert r0.shape == r1.shape and np.array_equal(r0, r1)
+
+
+def test_packed_leaves_19x19_do_not_change_the_games():
+    """The same on the deep-search shape (19x19: six boards per tower group,
+    k_select<12>): packed and slot-indexed network self-play play the same
+    games."""
+    from azalea_b200 import LockstepSelfPlay
+    from azalea_b200.network import HexNetwork
+
+    def play(pack):
+        torch.manual_seed(0)
+        net = HexNetwork(19, 2, 64).eval().cuda()
+        net.prepare_inference(torch.bfloat16)
+        sp = LockstepSelfPlay(net, num_games=10, board_size=19, simulations=60,
+                              search_batch_size=10, seed=7, streams=2, cuda_graph=False,
+                              pack_leaves=pack, nodes_per_game=200_000)
+        chosen = []
+        for _ in range(12):
+            sp.step_move()
+            chosen.append(sp.chosen.cpu().numpy().copy())
+        assert (sp.eng.status().cpu().numpy() == 0).all()
+        return np.stack(chosen), sp.counters()
+    c0, n0 = play(False)
+    c1, n1 = play(True)
+    assert np.array_equal(c0, c1) and n0 == n1
